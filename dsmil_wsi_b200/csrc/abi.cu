@@ -1,0 +1,522 @@
+// extern "C" entry points of libdsmil_b200.so (see include/dsmil_b200.h for the contract and the
+// reference spans each call replaces).  Host orchestration only; kernels live in *_kernels.cuh
+// and fwd_sm100.cuh.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+#include "common.cuh"
+#include "gemm_generic.cuh"
+#include "fwd_kernels.cuh"
+#include "bwd_kernels.cuh"
+
+namespace dsmil {
+
+static thread_local char g_err[512] = "";
+__device__ unsigned long long scratch_keys[kMaxC];  // sink for k_scores' arg-max by-product
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+  return DSMIL_ERR_CUDA;
+}
+void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+// ---- live kernel timing ------------------------------------------------------------------
+bool g_prof_on = false;
+struct ProfRec { int tag; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;       // recorded pairs since the last read
+static std::vector<ProfRec> g_prof_pool;  // recycled events
+static int g_prof_open[PROF_NTAGS];
+void prof_begin_impl(int tag, cudaStream_t st) {
+  if (g_prof.size() >= 16384) { g_prof_open[tag] = -1; return; }
+  ProfRec r;
+  if (!g_prof_pool.empty()) { r = g_prof_pool.back(); g_prof_pool.pop_back(); }
+  else { if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) { g_prof_open[tag] = -1; return; } }
+  r.tag = tag;
+  cudaEventRecord(r.a, st);
+  g_prof_open[tag] = static_cast<int>(g_prof.size());
+  g_prof.push_back(r);
+}
+void prof_end_impl(int tag, cudaStream_t st) {
+  const int i = g_prof_open[tag];
+  if (i >= 0 && i < static_cast<int>(g_prof.size())) cudaEventRecord(g_prof[i].b, st);
+}
+
+static int check_params(const dsmil_params_t* p, bool need_scores = false) {
+  DSMIL_REQUIRE(p != nullptr, "params is NULL");
+  DSMIL_REQUIRE(!need_scores || (p->Wi && p->bi), "NULL instance-classifier weights");
+  DSMIL_REQUIRE(p->D >= 1 && p->D <= DSMIL_MAX_D, "feature size D=%d outside [1,%d]", p->D, DSMIL_MAX_D);
+  DSMIL_REQUIRE(p->C >= 1 && p->C <= DSMIL_MAX_C, "output classes C=%d outside [1,%d]", p->C, DSMIL_MAX_C);
+  DSMIL_REQUIRE(p->W1 && p->b1 && p->Wf && p->bf, "NULL weight pointer");
+  DSMIL_REQUIRE(!p->nonlinear || (p->W2 && p->b2), "nonlinear q needs W2/b2");
+  DSMIL_REQUIRE(!p->passing_v || (p->Wv && p->bv), "passing_v needs Wv/bv");
+  return 0;
+}
+
+static inline int attend_ctas(int64_t N) {
+  const int64_t tiles = (N + kAttendRows - 1) / kAttendRows;
+  return static_cast<int>(tiles < 296 ? (tiles < 1 ? 1 : tiles) : 296);
+}
+
+struct FwdWs {
+  unsigned long long* keys;
+  float *Q, *H1, *V, *cand, *qmax, *recs, *rec;
+  int64_t* crit;
+  size_t bytes;
+};
+static FwdWs carve_fwd(const dsmil_params_t* p, int64_t N, void* ws, size_t cap, bool* ok) {
+  Carver c(ws, cap);
+  FwdWs w;
+  const int64_t n = N > 0 ? N : 1;
+  w.keys = c.take<unsigned long long>(kMaxC);
+  w.Q = c.take<float>(n * kQ);
+  w.H1 = p->nonlinear ? c.take<float>(n * kQ) : nullptr;
+  w.V = p->passing_v ? c.take<float>(n * p->D) : nullptr;
+  w.cand = c.take<float>(cand_floats(p->C));
+  w.qmax = c.take<float>(static_cast<size_t>(p->C) * kQ);
+  w.crit = c.take<int64_t>(kMaxC);
+  w.recs = c.take<float>(static_cast<size_t>(attend_ctas(N)) * rec_floats(p->C, p->D));
+  w.rec = c.take<float>(rec_floats(p->C, p->D));
+  w.bytes = c.off;
+  *ok = c.ok();
+  return w;
+}
+
+// ---- phase 1: scores + arg-max key + Q-MLP (+V) + candidate record --------------------------
+static int phase1_impl(const dsmil_params_t* p, const float* X, const float* xv, const float* classes_in,
+                       int64_t N, int64_t row_offset, float* classes, float* Q, float* H1, float* V,
+                       float* cand, unsigned long long* keys, cudaStream_t st) {
+  const int C = p->C, D = p->D;
+  DSMIL_CUDA_OK(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * kMaxC, st));
+  if (N > 0) {
+    if (classes_in) {
+      if (classes && classes != classes_in)
+        DSMIL_CUDA_OK(cudaMemcpyAsync(classes, classes_in, sizeof(float) * N * C, cudaMemcpyDeviceToDevice, st));
+      const int grid = static_cast<int>(std::min<int64_t>(ceil_div(N, 256), 296));
+      k_argmax<<<grid, 256, 0, st>>>(classes_in, N, C, keys);
+      DSMIL_LAUNCH_OK("k_argmax");
+    } else {
+      const size_t smem = sizeof(float) * C * D;
+      const int grid = static_cast<int>(std::min<int64_t>(ceil_div(N, 8), 148 * 8));
+      const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+      prof_begin(PROF_SCORES, st);
+      if (vec) {
+        if (smem > 48 * 1024)
+          DSMIL_CUDA_OK(cudaFuncSetAttribute(k_scores<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_scores<true><<<grid, 256, smem, st>>>(X, N, D, p->Wi, p->bi, C, classes, keys);
+      } else {
+        if (smem > 48 * 1024)
+          DSMIL_CUDA_OK(cudaFuncSetAttribute(k_scores<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_scores<false><<<grid, 256, smem, st>>>(X, N, D, p->Wi, p->bi, C, classes, keys);
+      }
+      prof_end(PROF_SCORES, st);
+      DSMIL_LAUNCH_OK("k_scores");
+    }
+    int rc;
+    prof_begin(PROF_QMLP, st);
+    if (p->nonlinear) {
+      if ((rc = launch_linear<ACT_RELU, false>(X, N, D, p->W1, p->b1, kQ, H1, nullptr, 0, st))) return rc;
+      if ((rc = launch_linear<ACT_TANH, false>(H1, N, kQ, p->W2, p->b2, kQ, Q, nullptr, 0, st))) return rc;
+    } else {
+      if ((rc = launch_linear<ACT_NONE, false>(X, N, D, p->W1, p->b1, kQ, Q, nullptr, 0, st))) return rc;
+    }
+    prof_end(PROF_QMLP, st);
+    if (p->passing_v) {
+      if ((rc = launch_linear<ACT_RELU, false>(xv ? xv : X, N, D, p->Wv, p->bv, D, V, nullptr, 0, st))) return rc;
+    }
+  }
+  const float* cls = classes_in ? classes_in : classes;
+  k_gather_cand<<<C, kQ, 0, st>>>(keys, cls, Q, N, C, row_offset, cand);
+  DSMIL_LAUNCH_OK("k_gather_cand");
+  return 0;
+}
+
+__global__ void k_empty_rec(float* rec, int C, int Dv) {
+  const size_t n = rec_floats(C, Dv);
+  for (size_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    rec[i] = (i < static_cast<size_t>(C)) ? -INFINITY : 0.f;
+}
+
+template <int CT>
+static int launch_attend_j(int J, int grid, cudaStream_t st, const float* V, int Dv, const float* Q, int64_t N,
+                           const float* qmax, int C, float* A, float* recs) {
+  switch (J) {
+    case 1: k_attend<CT, 1><<<grid, 256, 0, st>>>(V, Dv, Q, N, qmax, C, A, recs); break;
+    case 2: k_attend<CT, 2><<<grid, 256, 0, st>>>(V, Dv, Q, N, qmax, C, A, recs); break;
+    case 4: k_attend<CT, 4><<<grid, 256, 0, st>>>(V, Dv, Q, N, qmax, C, A, recs); break;
+    case 8: k_attend<CT, 8><<<grid, 256, 0, st>>>(V, Dv, Q, N, qmax, C, A, recs); break;
+    default: k_attend<CT, 16><<<grid, 256, 0, st>>>(V, Dv, Q, N, qmax, C, A, recs); break;
+  }
+  DSMIL_LAUNCH_OK("k_attend");
+  return 0;
+}
+
+// ---- phase 2: logits -> A (unnormalised), device-level (m, s, Bp) record ------------------------
+static int phase2_impl(const dsmil_params_t* p, const float* V, const float* Q, int64_t N, const float* qmax,
+                       float* A, float* rec, float* recs, cudaStream_t st) {
+  const int C = p->C, Dv = p->D;
+  if (N <= 0) {
+    k_empty_rec<<<4, 256, 0, st>>>(rec, C, Dv);
+    DSMIL_LAUNCH_OK("k_empty_rec");
+    return 0;
+  }
+  const int grid = attend_ctas(N);
+  int j = ceil_div(Dv, 256), J = 1;
+  while (J < j) J <<= 1;
+  int rc;
+  prof_begin(PROF_ATTEND, st);
+  if (C == 1) rc = launch_attend_j<1>(J, grid, st, V, Dv, Q, N, qmax, C, A, recs);
+  else if (C == 2) rc = launch_attend_j<2>(J, grid, st, V, Dv, Q, N, qmax, C, A, recs);
+  else if (C <= 4) rc = launch_attend_j<4>(J, grid, st, V, Dv, Q, N, qmax, C, A, recs);
+  else rc = launch_attend_j<8>(J, grid, st, V, Dv, Q, N, qmax, C, A, recs);
+  prof_end(PROF_ATTEND, st);
+  if (rc) return rc;
+  dim3 g2(C, ceil_div(Dv, 256));
+  k_combine_rec<<<g2, 256, 0, st>>>(recs, grid, C, Dv, rec);
+  DSMIL_LAUNCH_OK("k_combine_rec");
+  return 0;
+}
+
+static int phase3_impl(const dsmil_params_t* p, int64_t N, const float* rec, float* A, float* B, float* pred,
+                       cudaStream_t st) {
+  const int grid = static_cast<int>(std::min<int64_t>(std::max<int64_t>(ceil_div(N * p->C, 256), 1), 296));
+  prof_begin(PROF_FINAL, st);
+  k_finalize<<<grid, 256, 0, st>>>(rec, N, p->C, p->D, p->Wf, p->bf, A, B, pred);
+  prof_end(PROF_FINAL, st);
+  DSMIL_LAUNCH_OK("k_finalize");
+  return 0;
+}
+
+static int forward_impl(const dsmil_params_t* p, const float* X, const float* xv, const float* classes_in,
+                        int64_t N, float* classes, float* pred, float* A, float* B, int64_t* crit_idx,
+                        float* save_Q, float* save_H1, float* save_V, void* ws, size_t ws_bytes, cudaStream_t st) {
+  int rc = check_params(p, classes_in == nullptr);
+  if (rc) return rc;
+  DSMIL_REQUIRE(N >= 0 && N < 0xffffffffll, "N=%lld out of range", (long long)N);
+  if (N == 0) {
+    set_error("empty bag (N == 0): the reference raises IndexError at dsmil.py:53");
+    return DSMIL_ERR_EMPTY;
+  }
+  DSMIL_REQUIRE(X && pred && A && B && (classes || classes_in), "NULL tensor pointer");
+  bool ok;
+  FwdWs w = carve_fwd(p, N, ws, ws_bytes, &ok);
+  if (!ws || !ok) {
+    set_error("workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes);
+    return DSMIL_ERR_WORKSPACE;
+  }
+  float* Q = save_Q ? save_Q : w.Q;
+  float* H1 = p->nonlinear ? (save_H1 ? save_H1 : w.H1) : nullptr;
+  float* V = p->passing_v ? (save_V ? save_V : w.V) : nullptr;
+  if ((rc = phase1_impl(p, X, xv, classes_in, N, 0, classes, Q, H1, V, w.cand, w.keys, st))) return rc;
+  int64_t* crit = crit_idx ? crit_idx : w.crit;
+  k_merge_cand<<<p->C, kQ, 0, st>>>(w.cand, 1, p->C, w.qmax, crit);
+  DSMIL_LAUNCH_OK("k_merge_cand");
+  const float* Vv = p->passing_v ? V : X;
+  if ((rc = phase2_impl(p, Vv, Q, N, w.qmax, A, w.rec, w.recs, st))) return rc;
+  return phase3_impl(p, N, w.rec, A, B, pred, st);
+}
+
+}  // namespace dsmil
+
+using namespace dsmil;
+
+extern "C" {
+
+int dsmil_abi_version(void) { return DSMIL_ABI_VERSION; }
+const char* dsmil_last_error(void) { return g_err; }
+uint64_t dsmil_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int dsmil_forward_path(const dsmil_params_t* p, int64_t N) {
+  (void)p; (void)N;
+  return 1;
+}
+
+int dsmil_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return 0;
+}
+int dsmil_profile_read(double* ms_per_tag, uint64_t* launches_per_tag) {
+  DSMIL_REQUIRE(ms_per_tag && launches_per_tag, "NULL output");
+  for (int t = 0; t < PROF_NTAGS; ++t) { ms_per_tag[t] = 0.0; launches_per_tag[t] = 0; }
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ms_per_tag[r.tag] += ms;
+      launches_per_tag[r.tag] += 1;
+    }
+    g_prof_pool.push_back(r);
+  }
+  g_prof.clear();
+  cudaGetLastError();
+  return 0;
+}
+
+size_t dsmil_cand_floats(int32_t C) { return cand_floats(C); }
+size_t dsmil_rec_floats(int32_t C, int32_t Dv) { return rec_floats(C, Dv); }
+
+size_t dsmil_forward_workspace_bytes(const dsmil_params_t* p, int64_t N) {
+  if (!p || p->C < 1 || p->C > DSMIL_MAX_C || p->D < 1 || p->D > DSMIL_MAX_D || N < 0) return 0;
+  bool ok;
+  return carve_fwd(p, N, nullptr, 0, &ok).bytes;
+}
+size_t dsmil_shard_workspace_bytes(const dsmil_params_t* p, int64_t N_local) {
+  return dsmil_forward_workspace_bytes(p, N_local);
+}
+
+int dsmil_forward(const dsmil_params_t* p, const float* X, const float* x_for_v, int64_t N, float* classes,
+                  float* pred, float* A, float* B, int64_t* crit_idx, float* save_Q, float* save_H1,
+                  float* save_V, void* workspace, size_t workspace_bytes, void* stream) {
+  DSMIL_REQUIRE(classes != nullptr, "classes is NULL");
+  return forward_impl(p, X, x_for_v, nullptr, N, classes, pred, A, B, crit_idx, save_Q, save_H1, save_V,
+                      workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int dsmil_bag_forward(const dsmil_params_t* p, const float* X, const float* x_for_v, const float* classes_in,
+                      int64_t N, float* pred, float* A, float* B, int64_t* crit_idx, float* save_Q,
+                      float* save_H1, float* save_V, void* workspace, size_t workspace_bytes, void* stream) {
+  DSMIL_REQUIRE(classes_in != nullptr, "classes_in is NULL");
+  return forward_impl(p, X, x_for_v, classes_in, N, nullptr, pred, A, B, crit_idx, save_Q, save_H1, save_V,
+                      workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int dsmil_instance_scores(const dsmil_params_t* p, const float* X, int64_t N, float* classes, void* stream) {
+  DSMIL_REQUIRE(p && p->Wi && p->bi && p->C >= 1 && p->C <= DSMIL_MAX_C && p->D >= 1 && p->D <= DSMIL_MAX_D,
+                "bad params");
+  DSMIL_REQUIRE(N >= 0 && (N == 0 || (X && classes)), "NULL tensor pointer");
+  if (N == 0) return 0;
+  // The arg-max by-product goes to a scratch key slot that is simply ignored here.
+  unsigned long long* keys;
+  DSMIL_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&keys), scratch_keys));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = sizeof(float) * p->C * p->D;
+  const int grid = static_cast<int>(std::min<int64_t>(ceil_div(N, 8), 148 * 8));
+  const bool vec = (p->D % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  if (vec) {
+    if (smem > 48 * 1024)
+      DSMIL_CUDA_OK(cudaFuncSetAttribute(k_scores<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_scores<true><<<grid, 256, smem, st>>>(X, N, p->D, p->Wi, p->bi, p->C, classes, keys);
+  } else {
+    if (smem > 48 * 1024)
+      DSMIL_CUDA_OK(cudaFuncSetAttribute(k_scores<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_scores<false><<<grid, 256, smem, st>>>(X, N, p->D, p->Wi, p->bi, p->C, classes, keys);
+  }
+  DSMIL_LAUNCH_OK("k_scores");
+  return 0;
+}
+
+// ---- sharded phases -----------------------------------------------------------------------
+int dsmil_shard_phase1(const dsmil_params_t* p, const float* X, const float* x_for_v, const float* classes_in,
+                       int64_t N_local, int64_t row_offset, float* classes, float* Q, float* H1, float* V,
+                       float* cand_rec, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_params(p, classes_in == nullptr);
+  if (rc) return rc;
+  DSMIL_REQUIRE(N_local >= 0 && N_local < 0xffffffffll, "N_local out of range");
+  DSMIL_REQUIRE(cand_rec && (N_local == 0 || (X && Q && (classes || classes_in))), "NULL tensor pointer");
+  DSMIL_REQUIRE(N_local == 0 || !p->passing_v || V, "passing_v needs a V buffer");
+  bool ok;
+  FwdWs w = carve_fwd(p, N_local, workspace, workspace_bytes, &ok);
+  if (!workspace || !ok) {
+    set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+    return DSMIL_ERR_WORKSPACE;
+  }
+  float* h1 = p->nonlinear ? (H1 ? H1 : w.H1) : nullptr;
+  return phase1_impl(p, X, x_for_v, classes_in, N_local, row_offset, classes, Q, h1, V, cand_rec, w.keys,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int dsmil_shard_merge_candidates(int32_t C, const float* cand_recs, int32_t G, float* q_max, int64_t* crit_idx,
+                                 void* stream) {
+  DSMIL_REQUIRE(C >= 1 && C <= DSMIL_MAX_C && G >= 1 && cand_recs && q_max && crit_idx, "bad arguments");
+  k_merge_cand<<<C, kQ, 0, static_cast<cudaStream_t>(stream)>>>(cand_recs, G, C, q_max, crit_idx);
+  DSMIL_LAUNCH_OK("k_merge_cand");
+  return 0;
+}
+
+int dsmil_shard_phase2(const dsmil_params_t* p, const float* Xv, const float* Q, int64_t N_local,
+                       const float* q_max, float* A_logits, float* rec, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  DSMIL_REQUIRE(rec && q_max && (N_local == 0 || (Xv && Q && A_logits)), "NULL tensor pointer");
+  bool ok;
+  FwdWs w = carve_fwd(p, N_local, workspace, workspace_bytes, &ok);
+  if (!workspace || !ok) {
+    set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+    return DSMIL_ERR_WORKSPACE;
+  }
+  return phase2_impl(p, Xv, Q, N_local, q_max, A_logits, rec, w.recs, static_cast<cudaStream_t>(stream));
+}
+
+int dsmil_shard_merge_partials(int32_t C, int32_t Dv, const float* recs, int32_t G, float* rec_out, void* stream) {
+  DSMIL_REQUIRE(C >= 1 && C <= DSMIL_MAX_C && Dv >= 1 && G >= 1 && G <= kMaxRecs && recs && rec_out, "bad arguments");
+  dim3 g2(C, ceil_div(Dv, 256));
+  k_combine_rec<<<g2, 256, 0, static_cast<cudaStream_t>(stream)>>>(recs, G, C, Dv, rec_out);
+  DSMIL_LAUNCH_OK("k_combine_rec");
+  return 0;
+}
+
+int dsmil_shard_phase3(const dsmil_params_t* p, int64_t N_local, const float* rec_global, float* A, float* B,
+                       float* pred, void* stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  DSMIL_REQUIRE(rec_global && B && pred && (N_local == 0 || A), "NULL tensor pointer");
+  return phase3_impl(p, N_local, rec_global, A, B, pred, static_cast<cudaStream_t>(stream));
+}
+
+// ---- backward -----------------------------------------------------------------------------
+struct BwdWs {
+  float *dB, *dA, *tpart, *dqm, *dz2, *dz1, *tnpart, *cspart, *dzv, *tmp;
+  size_t bytes;
+};
+static BwdWs carve_bwd(const dsmil_params_t* p, int64_t N, int need_gX, void* ws, size_t cap, bool* ok) {
+  Carver c(ws, cap);
+  BwdWs w;
+  const int C = p->C, D = p->D;
+  const int64_t n = N > 0 ? N : 1;
+  w.dB = c.take<float>(static_cast<size_t>(C) * D);
+  w.dA = c.take<float>(n * C);
+  w.tpart = c.take<float>(296 * kMaxC);
+  w.dqm = c.take<float>(static_cast<size_t>(C) * kQ);
+  w.dz2 = c.take<float>(n * kQ);
+  w.dz1 = p->nonlinear ? c.take<float>(n * kQ) : nullptr;
+  size_t tn = tn_partial_floats(kQ, D, N);
+  tn = std::max(tn, tn_partial_floats(kQ, kQ, N));
+  tn = std::max(tn, tn_partial_floats(C, kQ, N));
+  tn = std::max(tn, tn_partial_floats(C, D, N));
+  if (p->passing_v) tn = std::max(tn, tn_partial_floats(D, D, N));
+  w.tnpart = c.take<float>(tn);
+  w.cspart = c.take<float>(static_cast<size_t>(296) * std::max(D, kQ));
+  w.dzv = p->passing_v ? c.take<float>(n * D) : nullptr;
+  w.tmp = (p->passing_v && need_gX) ? c.take<float>(n * D) : nullptr;
+  w.bytes = c.off;
+  *ok = c.ok();
+  return w;
+}
+
+size_t dsmil_backward_workspace_bytes(const dsmil_params_t* p, int64_t N, int need_gX) {
+  if (!p || p->C < 1 || p->C > DSMIL_MAX_C || p->D < 1 || p->D > DSMIL_MAX_D || N < 0) return 0;
+  bool ok;
+  return carve_bwd(p, N, need_gX, nullptr, 0, &ok).bytes;
+}
+
+int dsmil_backward(const dsmil_params_t* p, const float* X, const float* x_for_v, int64_t N, const float* Q,
+                   const float* H1, const float* V, const float* A, const float* B, const int64_t* crit_idx,
+                   const float* d_classes, const float* d_pred, const float* d_A, const float* d_B,
+                   const dsmil_grads_t* g, const float* v_mask, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  DSMIL_REQUIRE(N >= 1 && X && Q && A && B && crit_idx && g, "NULL tensor pointer or N < 1");
+  DSMIL_REQUIRE(!p->nonlinear || H1, "nonlinear q backward needs saved H1");
+  DSMIL_REQUIRE(!p->passing_v || V, "passing_v backward needs saved V");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = p->C, D = p->D;
+  bool ok;
+  BwdWs w = carve_bwd(p, N, g->gX != nullptr, workspace, workspace_bytes, &ok);
+  if (!workspace || !ok) {
+    set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+    return DSMIL_ERR_WORKSPACE;
+  }
+  const float* Vv = p->passing_v ? V : X;
+  const float* Xv = x_for_v ? x_for_v : X;
+  const int gs = static_cast<int>(std::min<int64_t>(ceil_div(N, 256), 296));
+
+  // bag classifier (dsmil.py:59-61) and B
+  k_bwd_bag<<<ceil_div(static_cast<int64_t>(C) * D, 256), 256, 0, st>>>(p->Wf, B, d_pred, d_B, C, D, w.dB, g->gWf,
+                                                                        g->gbf);
+  DSMIL_LAUNCH_OK("k_bwd_bag");
+  // instance classifier (dsmil.py:11): only rows with non-zero upstream grad contribute
+  if (g->gWi) {
+    if (d_classes) { if ((rc = launch_gemm_tn(d_classes, C, X, D, N, w.tnpart, g->gWi, st))) return rc; }
+    else DSMIL_CUDA_OK(cudaMemsetAsync(g->gWi, 0, sizeof(float) * C * D, st));
+  }
+  if (g->gbi) {
+    if (d_classes) { if ((rc = launch_colsum(d_classes, C, N, w.cspart, g->gbi, st))) return rc; }
+    else DSMIL_CUDA_OK(cudaMemsetAsync(g->gbi, 0, sizeof(float) * C, st));
+  }
+  // dA = V dB^T (+ upstream), softmax-over-instances backward (dsmil.py:56-57)
+  {
+    const size_t smem = sizeof(float) * C * D;
+    if (smem > 48 * 1024)
+      DSMIL_CUDA_OK(cudaFuncSetAttribute(k_rowdot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = static_cast<int>(std::min<int64_t>(ceil_div(N, 8), 148 * 8));
+    k_rowdot<<<grid, 256, smem, st>>>(Vv, N, D, w.dB, C, d_A, w.dA);
+    DSMIL_LAUNCH_OK("k_rowdot");
+  }
+  k_bwd_t_partial<<<gs, 256, 0, st>>>(A, w.dA, N, C, w.tpart);
+  DSMIL_LAUNCH_OK("k_bwd_t_partial");
+  k_bwd_dL<<<gs, 256, 0, st>>>(A, w.dA, N, C, w.tpart, gs);
+  DSMIL_LAUNCH_OK("k_bwd_dL");
+  const float* dL = w.dA;
+  // dq_max = dL^T Q  (dsmil.py:55), then dQ rows (+ the critical rows' share, dsmil.py:53-54)
+  if ((rc = launch_gemm_tn(dL, C, Q, kQ, N, w.tnpart, w.dqm, st))) return rc;
+  {
+    const int grid = static_cast<int>(std::min<int64_t>(ceil_div(N * kQ, 256), 148 * 8));
+    k_bwd_dq<<<grid, 256, 0, st>>>(dL, Q, w.dqm, crit_idx, N, C, p->nonlinear, w.dz2);
+    DSMIL_LAUNCH_OK("k_bwd_dq");
+  }
+  const float* dz1 = w.dz2;
+  if (p->nonlinear) {
+    if (g->gW2 && (rc = launch_gemm_tn(w.dz2, kQ, H1, kQ, N, w.tnpart, g->gW2, st))) return rc;
+    if (g->gb2 && (rc = launch_colsum(w.dz2, kQ, N, w.cspart, g->gb2, st))) return rc;
+    if ((rc = launch_linear<ACT_MASK_POS, true>(w.dz2, N, kQ, p->W2, nullptr, kQ, w.dz1, H1, 0, st))) return rc;
+    dz1 = w.dz1;
+  }
+  if (g->gW1 && (rc = launch_gemm_tn(dz1, kQ, X, D, N, w.tnpart, g->gW1, st))) return rc;
+  if (g->gb1 && (rc = launch_colsum(dz1, kQ, N, w.cspart, g->gb1, st))) return rc;
+
+  const int ge = static_cast<int>(std::min<int64_t>(ceil_div(N * D, 256), 148 * 8));
+  if (p->passing_v) {
+    k_bwd_dzv<<<ge, 256, 0, st>>>(A, w.dB, V, N, C, D, w.dzv);
+    DSMIL_LAUNCH_OK("k_bwd_dzv");
+    if (g->gWv && (rc = launch_gemm_tn(w.dzv, D, Xv, D, N, w.tnpart, g->gWv, st))) return rc;
+    if (g->gbv && (rc = launch_colsum(w.dzv, D, N, w.cspart, g->gbv, st))) return rc;
+  }
+  if (g->gX) {
+    if ((rc = launch_linear<ACT_NONE, true>(dz1, N, kQ, p->W1, nullptr, D, g->gX, nullptr, 0, st))) return rc;
+    k_bwd_dx_extra<<<ge, 256, 0, st>>>(d_classes, p->Wi, p->passing_v ? nullptr : A, w.dB, N, C, D, 1, g->gX);
+    DSMIL_LAUNCH_OK("k_bwd_dx_extra");
+    if (p->passing_v) {
+      if ((rc = launch_linear<ACT_NONE, true>(w.dzv, N, D, p->Wv, nullptr, D, w.tmp, nullptr, 0, st))) return rc;
+      k_axpy_mask<<<ge, 256, 0, st>>>(w.tmp, v_mask, N * D, g->gX);
+      DSMIL_LAUNCH_OK("k_axpy_mask");
+    }
+  }
+  return 0;
+}
+
+int dsmil_instance_scores_backward(const dsmil_params_t* p, const float* X, int64_t N, const float* d_classes,
+                                   float* gWi, float* gbi, float* gX, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  DSMIL_REQUIRE(p && p->Wi && p->C >= 1 && p->C <= DSMIL_MAX_C && p->D >= 1 && p->D <= DSMIL_MAX_D, "bad params");
+  DSMIL_REQUIRE(N >= 1 && X && d_classes, "NULL tensor pointer or N < 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = p->C, D = p->D;
+  Carver c(workspace, workspace_bytes);
+  float* tnpart = c.take<float>(tn_partial_floats(C, D, N));
+  float* cspart = c.take<float>(static_cast<size_t>(296) * kMaxC);
+  if (!workspace || !c.ok()) {
+    set_error("workspace too small: need %zu bytes, got %zu", c.off, workspace_bytes);
+    return DSMIL_ERR_WORKSPACE;
+  }
+  int rc;
+  if (gWi && (rc = launch_gemm_tn(d_classes, C, X, D, N, tnpart, gWi, st))) return rc;
+  if (gbi && (rc = launch_colsum(d_classes, C, N, cspart, gbi, st))) return rc;
+  if (gX) {
+    const int ge = static_cast<int>(std::min<int64_t>(ceil_div(N * D, 256), 148 * 8));
+    k_bwd_dx_extra<<<ge, 256, 0, st>>>(d_classes, p->Wi, nullptr, nullptr, N, C, D, 0, gX);
+    DSMIL_LAUNCH_OK("k_bwd_dx_extra");
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+"""Row-sharded forward of ONE giant bag over the ranks of a torch.distributed group
+(north_star: "patches of one giant bag shard across the 8 GPUs ...
+NCCL only for the per-class critical-instance max and the attention-weighted partial sums").
+
+One process per GPU.  Rank r owns the contiguous rows [offset_r, offset_r + N_r).  Per forward
+there are exactly two data-path collectives, both all-gathers of a few KB:
+    exchange 1: candidate record  (global idx, score, q row) per class     C*131 floats / rank
+    exchange 2: partial record    (m, s, unnormalised partial B) per class C*(2+D) floats / rank
+Everything else is local: phase1/2/3 of the C ABI (include/dsmil_b200.h).  classes and A stay
+sharded; prediction_bag, B and the critical indices are replicated.
+
+`ops` abstracts the five local steps so the exchange/merge logic can be exercised on CPU with
+gloo (tests/test_sharded_gloo.py injects an oracle-backed ops object; the product default is
+CudaShardOps, which has no fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from . import functional as Fn
+
+
+def shard_bounds(N: int, G: int) -> List[Tuple[int, int]]:
+    """Contiguous row blocks; the first N % G ranks get one extra row."""
+    base, rem = divmod(N, G)
+    out, lo = [], 0
+    for r in range(G):
+        hi = lo + base + (1 if r < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+class CudaShardOps:
+    """The five local steps on the current CUDA device through libdsmil_b200.so."""
+
+    def __init__(self, params: Sequence[Optional[torch.Tensor]]):
+        self.lib = _lib.load()
+        self.P = Fn.ParamPack(*params)
+        self.device = self.P.device
+
+    # sizes of the exchanged records (floats)
+    def cand_floats(self) -> int:
+        return int(self.lib.dsmil_cand_floats(self.P.C))
+
+    def rec_floats(self) -> int:
+        return int(self.lib.dsmil_rec_floats(self.P.C, self.P.D))
+
+    def new(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def _ws(self, N):
+        return Fn._workspace(self.lib.dsmil_shard_workspace_bytes(self.P.ref, N), self.device)
+
+    def phase1(self, X: torch.Tensor, row_offset: int):
+        P, N = self.P, int(X.shape[0])
+        X = Fn._check_feats(X, P.D) if N > 0 else X
+        with torch.cuda.device(self.device):
+            classes, Q = self.new(N, P.C), self.new(N, Fn.Q_DIM)
+            V = self.new(N, P.D) if P.passing_v else None
+            cand = self.new(self.cand_floats())
+            ws = self._ws(N)
+            rc = self.lib.dsmil_shard_phase1(P.ref, Fn._ptr(X), None, None, N, int(row_offset), Fn._ptr(classes),
+                                             Fn._ptr(Q), None, Fn._ptr(V), Fn._ptr(cand), Fn._ptr(ws), ws.numel(),
+                                             Fn._stream())
+            _lib.check(rc, "dsmil_shard_phase1")
+        return classes, Q, (V if P.passing_v else X), cand
+
+    def merge_candidates(self, cands: torch.Tensor, G: int):
+        with torch.cuda.device(self.device):
+            qmax = self.new(self.P.C, Fn.Q_DIM)
+            crit = self.new(self.P.C, dtype=torch.int64)
+            rc = self.lib.dsmil_shard_merge_candidates(self.P.C, Fn._ptr(cands), G, Fn._ptr(qmax), Fn._ptr(crit),
+                                                       Fn._stream())
+            _lib.check(rc, "dsmil_shard_merge_candidates")
+        return qmax, crit
+
+    def phase2(self, Vv: torch.Tensor, Q: torch.Tensor, qmax: torch.Tensor):
+        P, N = self.P, int(Q.shape[0])
+        with torch.cuda.device(self.device):
+            A = self.new(N, P.C)
+            rec = self.new(self.rec_floats())
+            ws = self._ws(N)
+            rc = self.lib.dsmil_shard_phase2(P.ref, Fn._ptr(Vv), Fn._ptr(Q), N, Fn._ptr(qmax), Fn._ptr(A),
+                                             Fn._ptr(rec), Fn._ptr(ws), ws.numel(), Fn._stream())
+            _lib.check(rc, "dsmil_shard_phase2")
+        return A, rec
+
+    def merge_partials(self, recs: torch.Tensor, G: int):
+        with torch.cuda.device(self.device):
+            out = self.new(self.rec_floats())
+            rc = self.lib.dsmil_shard_merge_partials(self.P.C, self.P.D, Fn._ptr(recs), G, Fn._ptr(out), Fn._stream())
+            _lib.check(rc, "dsmil_shard_merge_partials")
+        return out
+
+    def phase3(self, rec: torch.Tensor, A: torch.Tensor):
+        P, N = self.P, int(A.shape[0])
+        with torch.cuda.device(self.device):
+            B, pred = self.new(1, P.C, P.D), self.new(1, P.C)
+            rc = self.lib.dsmil_shard_phase3(P.ref, N, Fn._ptr(rec), Fn._ptr(A), Fn._ptr(B), Fn._ptr(pred),
+                                             Fn._stream())
+            _lib.check(rc, "dsmil_shard_phase3")
+        return A, B, pred
+
+
+def _all_gather(rec: torch.Tensor, group) -> Tuple[torch.Tensor, int]:
+    import torch.distributed as dist
+    G = dist.get_world_size(group)
+    out = torch.empty(G * rec.numel(), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(out, rec.contiguous(), group=group)
+    return out, G
+
+
+@torch.no_grad()
+def sharded_forward(ops, X_local: torch.Tensor, row_offset: int, group=None):
+    """Forward of one bag whose rows are spread over the ranks of `group`.
+    Returns (classes_local[N_r,C], prediction_bag[1,C], A_local[N_r,C], B[1,C,D], crit_idx[C])."""
+    classes, Q, Vv, cand = ops.phase1(X_local, row_offset)
+    cands, G = _all_gather(cand, group)                     # exchange 1
+    qmax, crit = ops.merge_candidates(cands, G)
+    A, rec = ops.phase2(Vv, Q, qmax)
+    recs, G = _all_gather(rec, group)                       # exchange 2
+    rec_g = ops.merge_partials(recs, G)
+    A, B, pred = ops.phase3(rec_g, A)
+    return classes, pred, A, B, crit
+
+
+@torch.no_grad()
+def virtual_sharded_forward(ops, X: torch.Tensor, G: int):
+    """Same algebra with G logical shards on ONE device and the collectives replaced by local
+    concatenation -- lets the sharding logic be validated without G GPUs."""
+    bounds = shard_bounds(int(X.shape[0]), G)
+    loc = [ops.phase1(X[lo:hi], lo) for lo, hi in bounds]
+    cands = torch.cat([l[3] for l in loc])
+    qmax, crit = ops.merge_candidates(cands, G)
+    part = [ops.phase2(l[2], l[1], qmax) for l in loc]
+    rec_g = ops.merge_partials(torch.cat([p[1] for p in part]), G)
+    outs = [ops.phase3(rec_g, p[0]) for p in part]
+    return (torch.cat([l[0] for l in loc]), outs[0][2], torch.cat([o[0] for o in outs]), outs[0][1], crit)
+
+
+def milnet_params(milnet) -> Tuple[Optional[torch.Tensor], ...]:
+    """The ten parameter tensors of a MILNet(FCLayer|IClassifier, BClassifier) in ABI order."""
+    lin = milnet.i_classifier._linear()
+    bc = milnet.b_classifier
+    W1, b1, W2, b2 = bc._q_params()
+    Wv, bv, _ = bc._v_params()
+    return (lin.weight, lin.bias, W1, b1, W2, b2, Wv, bv, bc.fcc.weight, bc.fcc.bias)
+
+
+@torch.no_grad()
+def sharded_forward_bags(ops, X_locals: Sequence[torch.Tensor], row_offsets: Sequence[int], group=None):
+    """A batch of giant bags, each row-sharded over the group: the per-bag records are packed so the
+    whole batch costs TWO collectives (not two per bag) -- at a few KB per record the exchange is
+    latency-bound, so batching is what keeps NVLink out of the critical path."""
+    nb = len(X_locals)
+    p1 = [ops.phase1(x, off) for x, off in zip(X_locals, row_offsets)]
+    cand_all, G = _all_gather(torch.cat([t[3] for t in p1]), group)          # exchange 1 (all bags)
+    cand_all = cand_all.view(G, nb, -1)
+    outs_mid = []
+    for b in range(nb):
+        qmax, crit = ops.merge_candidates(cand_all[:, b].contiguous(), G)
+        A, rec = ops.phase2(p1[b][2], p1[b][1], qmax)
+        outs_mid.append((A, rec, crit))
+    rec_all, G = _all_gather(torch.cat([t[1] for t in outs_mid]), group)      # exchange 2 (all bags)
+    rec_all = rec_all.view(G, nb, -1)
+    outs = []
+    for b in range(nb):
+        rec_g = ops.merge_partials(rec_all[:, b].contiguous(), G)
+        A, B, pred = ops.phase3(rec_g, outs_mid[b][0])
+        outs.append((p1[b][0], pred, A, B, outs_mid[b][2]))
+    return outs

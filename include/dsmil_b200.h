@@ -1,0 +1,157 @@
+/*
+ * dsmil_b200.h -- C ABI of libdsmil_b200.so: the DSMIL per-slide aggregator hot path on B200 (sm_100a).
+ *
+ * The reference (binli123/dsmil-wsi) is pure Python/PyTorch and has no FFI of its own; the
+ * "interface" each entry point replaces is therefore a span of reference Python, cited per
+ * function as file:line into the reference repo.  INTEGRATION.md shows the ctypes binding a
+ * maintainer adds (it is the one dsmil_wsi_b200/_lib.py ships).
+ *
+ * Conventions
+ *  - Every pointer named *_dev / documented "device" is a CUDA device pointer on the CURRENT
+ *    device; the library never allocates per call: the caller (PyTorch's caching allocator in
+ *    our host mirror) owns every buffer including the workspace.
+ *  - All tensors are fp32, row-major, contiguous.  Indices are int64.
+ *  - Calls are asynchronous on `stream` (a cudaStream_t passed as void*); no host sync inside.
+ *  - Return value: 0 on success, a negative dsmil_status_t otherwise; dsmil_last_error() gives
+ *    a thread-local message (CUDA error string included).
+ *  - No CPU fallback exists: without a CUDA device every compute entry point returns
+ *    DSMIL_ERR_CUDA.
+ */
+#ifndef DSMIL_B200_H_
+#define DSMIL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSMIL_ABI_VERSION 1
+#define DSMIL_Q 128      /* query width, hard-coded in the reference: dsmil.py:31,33 */
+#define DSMIL_MAX_C 8    /* output classes supported by the fused kernels (reference uses 1, 2) */
+#define DSMIL_MAX_D 4096 /* feature size bound (reference: 166/230/512/1024/2048) */
+
+typedef enum dsmil_status {
+  DSMIL_OK = 0,
+  DSMIL_ERR_ARG = -1,       /* bad shape / null pointer / unsupported size */
+  DSMIL_ERR_WORKSPACE = -2, /* workspace too small */
+  DSMIL_ERR_CUDA = -3,      /* CUDA runtime error (see dsmil_last_error) */
+  DSMIL_ERR_EMPTY = -4      /* N == 0 on a single-device forward (reference raises IndexError) */
+} dsmil_status_t;
+
+/* Parameter block == the state_dict of MILNet(FCLayer|IClassifier, BClassifier)
+ * (dsmil.py:6-12,14-25,27-44; key names in SURVEY.md §8 a3).  Device pointers. */
+typedef struct dsmil_params {
+  int32_t D;         /* input_size / feature_size */
+  int32_t C;         /* output_class */
+  int32_t nonlinear; /* 1: q = Linear(D,128)-ReLU-Linear(128,128)-Tanh (dsmil.py:31); 0: Linear(D,128) (:33) */
+  int32_t passing_v; /* 1: v = Dropout-Linear(D,D)-ReLU (dsmil.py:35-39); 0: Identity (:41) */
+  const float* Wi;   /* [C,D]    i_classifier.fc(.0).weight */
+  const float* bi;   /* [C]      i_classifier.fc(.0).bias   */
+  const float* W1;   /* [128,D]  b_classifier.q.0.weight  (or q.weight when !nonlinear) */
+  const float* b1;   /* [128] */
+  const float* W2;   /* [128,128] b_classifier.q.2.weight (NULL when !nonlinear) */
+  const float* b2;   /* [128] */
+  const float* Wv;   /* [D,D]    b_classifier.v.1.weight  (NULL when !passing_v) */
+  const float* bv;   /* [D] */
+  const float* Wf;   /* [C,C,D]  b_classifier.fcc.weight (Conv1d(C,C,kernel_size=D), dsmil.py:44) */
+  const float* bf;   /* [C] */
+} dsmil_params_t;
+
+/* Gradient block: same shapes as dsmil_params_t's tensors; device pointers, OVERWRITTEN
+ * (not accumulated).  Any pointer may be NULL to skip that gradient. */
+typedef struct dsmil_grads {
+  float* gWi; float* gbi;
+  float* gW1; float* gb1;
+  float* gW2; float* gb2;
+  float* gWv; float* gbv;
+  float* gWf; float* gbf;
+  float* gX;  /* [N,D] gradient w.r.t. the features, NULL unless the caller needs it */
+} dsmil_grads_t;
+
+int dsmil_abi_version(void);
+const char* dsmil_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t dsmil_launch_count(void);
+/* Live per-kernel timing for the roofline report (bench.py): when enabled, tagged launches are
+ * bracketed by CUDA events on the launching stream.  dsmil_profile_read synchronises those events,
+ * returns summed milliseconds and launch counts per tag (arrays of 8: 0 scores, 1 q-mlp, 2 attend,
+ * 3 finalize, 4 fused tcgen05 kernel) and resets the log.  Not thread-safe; bench use only. */
+int dsmil_profile_enable(int on);
+int dsmil_profile_read(double* ms_per_tag, uint64_t* launches_per_tag);
+/* Which kernel family the forward would use for (D,C): 1 = generic fp32 FFMA, 2 = sm_100a tcgen05. */
+int dsmil_forward_path(const dsmil_params_t* p, int64_t N);
+
+/* ---- single-device forward ------------------------------------------------------------
+ * Replaces MILNet.forward with an FCLayer/IClassifier.fc instance stream:
+ *   dsmil.py:70-74 (composition), :10-12 / :24 (scores), :46-62 (aggregator).
+ * in : X[N,D] device.  out: classes[N,C], pred[1,C], A[N,C], B[1,C,D], crit_idx[C] (the row
+ * dsmil.py:52-53 selects; lowest index on ties).  save_Q[N,128] / save_H1[N,128] /
+ * save_V[N,D] are optional (NULL) buffers that keep the activations backward needs.
+ * x_for_v: when passing_v, the features AFTER the caller applied the dropout mask of
+ * dsmil.py:36 (NULL = same as X, i.e. eval mode or p=0). */
+size_t dsmil_forward_workspace_bytes(const dsmil_params_t* p, int64_t N);
+int dsmil_forward(const dsmil_params_t* p, const float* X, const float* x_for_v, int64_t N,
+                  float* classes, float* pred, float* A, float* B, int64_t* crit_idx,
+                  float* save_Q, float* save_H1, float* save_V,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Call form (2)+(3) of the boundary: the callers in attention_map.py:74,85 /
+ * testing_tcga.py:72,83 run the instance classifier and the bag classifier separately.
+ * dsmil_instance_scores == IClassifier.fc / FCLayer.fc (dsmil.py:11,24).
+ * dsmil_bag_forward     == BClassifier.forward(feats, c) (dsmil.py:46-62) on GIVEN scores c. */
+int dsmil_instance_scores(const dsmil_params_t* p, const float* X, int64_t N, float* classes, void* stream);
+/* Reverse of dsmil_instance_scores: gWi[C,D] = d_classes^T X, gbi[C] = column sums, and
+ * (optional) gX[N,D] = d_classes Wi.  Workspace: dsmil_backward_workspace_bytes(p, N, 0). */
+int dsmil_instance_scores_backward(const dsmil_params_t* p, const float* X, int64_t N, const float* d_classes,
+                                   float* gWi, float* gbi, float* gX,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+int dsmil_bag_forward(const dsmil_params_t* p, const float* X, const float* x_for_v, const float* classes_in,
+                      int64_t N, float* pred, float* A, float* B, int64_t* crit_idx,
+                      float* save_Q, float* save_H1, float* save_V,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- single-device backward ------------------------------------------------------------
+ * Reverse of dsmil_forward for upstream gradients d_classes[N,C], d_pred[C], d_A[N,C],
+ * d_B[C,Dv] (each may be NULL == zero).  This is what autograd does through dsmil.py:46-62
+ * for the callers' loss (train_tcga.py:67-72, train_mil.py:50-56); arg-max indices are
+ * non-differentiable, q_max shares the rows of Q.  Needs the forward's saved Q, H1, V, A, B,
+ * crit_idx. */
+size_t dsmil_backward_workspace_bytes(const dsmil_params_t* p, int64_t N, int need_gX);
+int dsmil_backward(const dsmil_params_t* p, const float* X, const float* x_for_v, int64_t N,
+                   const float* Q, const float* H1, const float* V, const float* A, const float* B,
+                   const int64_t* crit_idx,
+                   const float* d_classes, const float* d_pred, const float* d_A, const float* d_B,
+                   const dsmil_grads_t* grads, const float* v_mask,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- row-sharded forward (one giant bag over G ranks) -----------
+ * Each rank owns rows [row_offset, row_offset+N_local).  Two exchange steps (all-gather of a
+ * few KB, done by the caller with NCCL between the phases):
+ *   phase1 -> cand record   [dsmil_cand_floats(C)]  = score[C] | idx[C] (int64 bits) | qrow[C,128]
+ *   merge_candidates(G records) -> q_max[C,128], crit_idx[C]
+ *   phase2 -> partial record [dsmil_rec_floats(C,Dv)] = m[C] | s[C] | Bpartial[C,Dv]
+ *   merge_partials(G records)  -> global record
+ *   phase3 -> A (normalised, local rows), B[1,C,Dv], pred[1,C] (replicated)
+ * N_local may be 0 on a rank.  dsmil_forward == these five calls with G == 1. */
+size_t dsmil_cand_floats(int32_t C);
+size_t dsmil_rec_floats(int32_t C, int32_t Dv);
+size_t dsmil_shard_workspace_bytes(const dsmil_params_t* p, int64_t N_local);
+int dsmil_shard_phase1(const dsmil_params_t* p, const float* X, const float* x_for_v, const float* classes_in,
+                       int64_t N_local, int64_t row_offset,
+                       float* classes, float* Q, float* H1, float* V, float* cand_rec,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int dsmil_shard_merge_candidates(int32_t C, const float* cand_recs, int32_t G, float* q_max, int64_t* crit_idx,
+                                 void* stream);
+int dsmil_shard_phase2(const dsmil_params_t* p, const float* Xv, const float* Q, int64_t N_local,
+                       const float* q_max, float* A_logits, float* rec,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int dsmil_shard_merge_partials(int32_t C, int32_t Dv, const float* recs, int32_t G, float* rec_out, void* stream);
+int dsmil_shard_phase3(const dsmil_params_t* p, int64_t N_local, const float* rec_global,
+                       float* A, float* B, float* pred, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSMIL_B200_H_ */

@@ -1,0 +1,257 @@
+"""GPU parity: the CUDA path (through the reference-facing modules -> ctypes -> C ABI) against
+  (1) the golden fixtures produced by the unmodified reference, and
+  (2) the fp64 oracle on seeded inputs at BASELINE.json sizes,
+plus size-independent properties at full size.  Tolerances (fp32 path, stated once):
+  arg-max indices: bit-exact (tie-free inputs)        classes: 2e-6 rel-to-max
+  A: 2e-5 rel-to-column-max   B: 1e-5 rel-to-max      bag logits: 1e-5 * max(|logit|, |Wf|.|B|)
+  gradients: 5e-4 rel-to-tensor-max vs fp32 autograd through the reference (its own noise ~1e-4)
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden, rel_to_max
+from helpers import build_net, caller_loss, grad_name, pred_tolerance_ok
+from oracle import dsmil_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL_CLS, TOL_A, TOL_B, TOL_PRED, TOL_GRAD = 2e-6, 2e-5, 1e-5, 1e-5, 5e-4
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _check_forward(out, ref_classes, ref_pred, ref_A, ref_B, ref_idx, p, idx=None, tag=""):
+    classes, pred, A, B = (_np(t) for t in out)
+    N, C, D = ref_A.shape[0], p.C, p.D
+    assert classes.shape == (N, C) and pred.shape == (1, C) and A.shape == (N, C) and B.shape == (1, C, B.shape[2])
+    if idx is not None:
+        assert np.array_equal(_np(idx), ref_idx), (tag, _np(idx), ref_idx)
+    assert rel_to_max(classes, ref_classes) < TOL_CLS, (tag, "classes", rel_to_max(classes, ref_classes))
+    for k in range(C):
+        r = rel_to_max(A[:, k], ref_A[:, k])
+        assert r < TOL_A, (tag, "A", k, r)
+    assert rel_to_max(B, ref_B) < TOL_B, (tag, "B", rel_to_max(B, ref_B))
+    ok, err = pred_tolerance_ok(pred, ref_pred, p, ref_B, TOL_PRED)
+    assert ok, (tag, "pred", err, pred, ref_pred)
+    assert np.allclose(A.sum(0), 1.0, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_forward_vs_reference_golden(name):
+    g, p, X = load_golden(name)
+    net = build_net(p).eval()
+    x = torch.from_numpy(X).cuda()
+    with torch.no_grad():
+        out = net(x)
+        idx = net.critical_instances(x)
+    _check_forward(out, g["classes"], g["pred"], g["A"], g["B"], g["idx"], p, idx, name)
+    # and against the fp64 truth
+    t = orc.forward(X, p)
+    _check_forward(out, t.classes, t.prediction_bag, t.A, t.B, t.idx, p, idx, name + "/f64")
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_backward_vs_autograd_through_reference(name):
+    g, p, X = load_golden(name)
+    net = build_net(p).eval()   # eval: dropout off, as in the fixture
+    need_dx = "g_X" in g
+    x = torch.from_numpy(X).cuda().requires_grad_(need_dx)
+    classes, pred, A, B = net(x)
+    y = torch.from_numpy(g["y"]).cuda()
+    loss = caller_loss(classes, pred, y)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 3e-6 * max(1.0, abs(float(g["loss"])))
+    named = dict(net.named_parameters())
+    for key in [k for k in g if k.startswith("g_") and k != "g_X"]:
+        got = _np(named[grad_name(key[2:], p.nonlinear)].grad)
+        r = rel_to_max(got, g[key])
+        assert got.shape == g[key].shape and r < TOL_GRAD, (name, key, r)
+    if need_dx:
+        assert rel_to_max(_np(x.grad), g["g_X"]) < TOL_GRAD
+    # tighter: vs the fp64 manual backward of the oracle
+    t = orc.forward(X, p)
+    _, d_cls, d_pred = orc.caller_loss_grads(t, g["y"])
+    tg = orc.backward(X, p, t, d_cls, d_pred, need_dX=need_dx)
+    for k, v in tg.items():
+        got = _np(x.grad) if k == "X" else _np(named[grad_name(k, p.nonlinear)].grad)
+        assert rel_to_max(got, v) < 5e-5, (name, k, rel_to_max(got, v))
+
+
+@pytest.mark.parametrize("N,C,kind,wseed", [(8192, 2, "uniform", 1), (10000, 2, "uniform", 2), (10000, 1, "normal", 3),
+                                            (15000, 1, "uniform", 4), (100000, 2, "uniform", 5)])
+def test_forward_vs_oracle_at_baseline_sizes(N, C, kind, wseed):
+    p = orc.random_params(512, C, 200 + wseed, scale=2.0)
+    X = orc.synthetic_bag(N, 512, 300 + wseed, kind)
+    t = orc.forward(X, p)
+    s = np.sort(t.classes, axis=0)
+    assert np.all(s[-1] - s[-2] > 1e-5)           # tie-free draw
+    net = build_net(p).eval()
+    x = torch.from_numpy(X).cuda()
+    with torch.no_grad():
+        out = net(x)
+        idx = net.critical_instances(x)
+    _check_forward(out, t.classes, t.prediction_bag, t.A, t.B, t.idx, p, idx, f"N{N}C{C}")
+
+
+def test_camelyon_shape_fwd_bwd_vs_oracle():
+    """BASELINE config 3: N=15000, D=512, C=1, fwd+bwd with the train_tcga.py:67-72 loss."""
+    p = orc.random_params(512, 1, 77, scale=2.0)
+    X = orc.synthetic_bag(15000, 512, 78, "uniform")
+    y = np.array([1.0], np.float32)
+    net = build_net(p).train()
+    classes, pred, A, B = net(torch.from_numpy(X).cuda())
+    loss = caller_loss(classes, pred, torch.from_numpy(y).cuda())
+    loss.backward()
+    t = orc.forward(X, p)
+    tl, d_cls, d_pred = orc.caller_loss_grads(t, y)
+    assert abs(loss.item() - tl) < 3e-6
+    tg = orc.backward(X, p, t, d_cls, d_pred)
+    named = dict(net.named_parameters())
+    for k, v in tg.items():
+        r = rel_to_max(_np(named[grad_name(k, True)].grad), v)
+        assert r < 5e-5, (k, r)
+
+
+def test_split_call_forms_compose_to_fused():
+    """attention_map.py:74,85: i_classifier(x) then b_classifier(feats, classes) == milnet(x)."""
+    g, p, X = load_golden("shipped_tcga")
+    net = build_net(p).eval()
+    x = torch.from_numpy(X).cuda()
+    with torch.no_grad():
+        c1, p1, A1, B1 = net(x)
+        feats, c2 = net.i_classifier(x)
+        p2, A2, B2 = net.b_classifier(feats, c2)
+    assert feats is x
+    assert torch.equal(c1, c2) and torch.equal(A1, A2) and torch.equal(B1, B2) and torch.equal(p1, p2)
+
+
+def test_iclassifier_backbone_path_and_rekeyed_weights():
+    """testing_tcga.py:141-144: FCLayer.fc.0 weights re-keyed into IClassifier.fc, backbone in front."""
+    import dsmil as mil
+    g, p, X = load_golden("rand_d512_c2")
+    net = build_net(p).eval()
+    ic = mil.IClassifier(torch.nn.Flatten(), 512, 2)
+    sd = net.state_dict()
+    ic.load_state_dict({"fc.weight": sd["i_classifier.fc.0.weight"], "fc.bias": sd["i_classifier.fc.0.bias"]})
+    net2 = mil.MILNet(ic, net.b_classifier).cuda().eval()
+    x = torch.from_numpy(X).cuda()
+    with torch.no_grad():
+        a = net(x)
+        b = net2(x.view(-1, 8, 8, 8))
+        feats, c = net2.i_classifier(x.view(-1, 8, 8, 8))
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    assert feats.shape == (X.shape[0], 512) and torch.equal(c, a[0])
+
+
+def test_ties_and_permutation_properties():
+    p = orc.random_params(64, 2, 5)
+    X = orc.synthetic_bag(500, 64, 6, "normal")
+    X[77] = X[400] = X[13]                       # three identical rows -> exact ties if they win
+    p.Wi[0] = 0; p.bi[0] = 0                      # class 0: every score equal -> index 0 must win
+    net = build_net(p).eval()
+    x = torch.from_numpy(X).cuda()
+    with torch.no_grad():
+        classes, pred, A, B = net(x)
+        idx = _np(net.critical_instances(x))
+    c = _np(classes)
+    assert idx[0] == 0
+    assert c[idx[1], 1] == c[:, 1].max() and idx[1] == int(np.argmax(c[:, 1]))   # lowest index among maxima
+    # permutation: A permutes with the rows, B / logits invariant (up to summation order)
+    perm = torch.randperm(500, generator=torch.Generator().manual_seed(0)).cuda()
+    p.Wi[0] = orc.random_params(64, 2, 9).Wi[0]
+    net = build_net(p).eval()
+    with torch.no_grad():
+        c1, p1, A1, B1 = net(x)
+        c2, p2, A2, B2 = net(x[perm])
+    assert torch.equal(c1[perm], c2)
+    assert rel_to_max(_np(A2), _np(A1[perm])) < 1e-6
+    assert rel_to_max(_np(B2), _np(B1)) < 1e-6 and rel_to_max(_np(p2), _np(p1)) < 1e-5
+
+
+def test_train_mode_dropout_in_v_matches_masked_oracle():
+    """dsmil.py:36: Dropout inside v; the mask we draw is applied exactly like the reference applies its own."""
+    p = orc.random_params(96, 2, 21, passing_v=True)
+    X = orc.synthetic_bag(200, 96, 22, "normal")
+    net = build_net(p, dropout_v=0.3).train()
+    x = torch.from_numpy(X).cuda().requires_grad_(True)
+    torch.manual_seed(1234)
+    classes, pred, A, B = net(x)
+    torch.manual_seed(1234)
+    mask = _np(torch.nn.functional.dropout(torch.ones_like(x), 0.3, True))
+    assert 0.2 < (mask == 0).mean() < 0.4
+    t = orc.forward(X, p, v_mask=mask)
+    _check_forward((classes, pred, A, B), t.classes, t.prediction_bag, t.A, t.B, t.idx, p, None, "dropout_v")
+    y = np.array([1.0, 0.0], np.float32)
+    caller_loss(classes, pred, torch.from_numpy(y).cuda()).backward()
+    _, d_cls, d_pred = orc.caller_loss_grads(t, y)
+    tg = orc.backward(X, p, t, d_cls, d_pred, need_dX=True, v_mask=mask)
+    named = dict(net.named_parameters())
+    for k, v in tg.items():
+        got = _np(x.grad) if k == "X" else _np(named[grad_name(k, True)].grad)
+        assert rel_to_max(got, v) < 5e-5, (k, rel_to_max(got, v))
+
+
+def test_upstream_grads_on_A_and_B_are_honoured():
+    g, p, X = load_golden("musk_d166_n7")
+    net = build_net(p).eval()
+    x = torch.from_numpy(X).cuda()
+    classes, pred, A, B = net(x)
+    wA = torch.randn_like(A); wB = torch.randn_like(B); wc = torch.randn_like(classes)
+    ((A * wA).sum() + (B * wB).sum() + (classes * wc).sum() + pred.sum()).backward()
+    t = orc.forward(X, p)
+    tg = orc.backward(X, p, t, _np(wc), np.ones(p.C), d_A=_np(wA), d_B=_np(wB))
+    named = dict(net.named_parameters())
+    for k, v in tg.items():
+        assert rel_to_max(_np(named[grad_name(k, True)].grad), v) < 5e-5, k
+
+
+def test_short_training_run_tracks_cpu_autograd():
+    """train_mil.py:42-58 shaped loop (musk1-like: D=166, C=1, tiny bags), 12 Adam steps:
+    our module on the GPU vs the same algebra under torch-CPU autograd."""
+    rng = np.random.default_rng(0)
+    p0 = orc.random_params(166, 1, 31)
+    bags = [(orc.synthetic_bag(int(rng.integers(2, 40)), 166, 500 + i, "normal"), float(i % 2)) for i in range(12)]
+    net = build_net(p0).train()
+    opt = torch.optim.Adam(net.parameters(), lr=2e-4, betas=(0.5, 0.9), weight_decay=5e-3)
+    # CPU twin built from the oracle's TorchPort algebra but differentiable
+    import torch.nn.functional as F
+    W = {k: torch.tensor(getattr(p0, k), requires_grad=True) for k in ("Wi", "bi", "W1", "b1", "W2", "b2", "Wf", "bf")}
+    order = ["Wi", "bi", "W1", "b1", "W2", "b2", "Wf", "bf"]
+    opt2 = torch.optim.Adam([W[k] for k in order], lr=2e-4, betas=(0.5, 0.9), weight_decay=5e-3)
+
+    def twin(x):
+        c = F.linear(x, W["Wi"], W["bi"])
+        q = lambda z: torch.tanh(F.linear(torch.relu(F.linear(z, W["W1"], W["b1"])), W["W2"], W["b2"]))
+        Q = q(x)
+        idx = torch.sort(c, 0, descending=True).indices[0]
+        A = torch.softmax(Q @ q(x[idx]).t() / torch.sqrt(torch.tensor(128.0)), 0)
+        Bm = A.t() @ x
+        return c, F.conv1d(Bm.unsqueeze(0), W["Wf"], W["bf"]).view(1, -1)
+
+    for X, y in bags:
+        yt = torch.tensor([y])
+        opt.zero_grad(); opt2.zero_grad()
+        c, pr, _, _ = net(torch.from_numpy(X).cuda())
+        l1 = caller_loss(c, pr, yt.cuda()); l1.backward(); opt.step()
+        c2, pr2 = twin(torch.from_numpy(X))
+        l2 = caller_loss(c2, pr2, yt); l2.backward(); opt2.step()
+        assert abs(l1.item() - l2.item()) < 2e-5, (l1.item(), l2.item())
+    sd = net.state_dict()
+    assert rel_to_max(_np(sd["b_classifier.q.0.weight"]), W["W1"].detach().numpy()) < 1e-4
+
+
+def test_errors_are_loud():
+    import dsmil as mil
+    net = mil.MILNet(mil.FCLayer(32, 1), mil.BClassifier(32, 1)).cuda()
+    with pytest.raises(IndexError):
+        net(torch.empty(0, 32, device="cuda"))
+    with pytest.raises(ValueError):
+        net(torch.randn(4, 31, device="cuda"))
+    with pytest.raises(TypeError):
+        net(torch.randn(4, 32, device="cuda").double())
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        net(torch.randn(4, 32))

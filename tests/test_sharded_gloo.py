@@ -1,0 +1,146 @@
+"""N>1 host logic on CPU: world_size-2 (and 3) gloo groups run dsmil_wsi_b200.sharded.sharded_forward
+with an oracle-backed `ops` object standing in for the CUDA phases (test infrastructure), so the
+exchange / merge / record layouts of the multi-GPU path are covered without GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import load_golden, rel_to_max
+from oracle import dsmil_oracle as orc
+
+
+class OracleShardOps:
+    """numpy restatement of the five local steps with the library's record layouts
+    (cand: idx[C] int64 | score[C] | qrow[C,128];  rec: m[C] | s[C] | Bp[C,Dv])."""
+
+    def __init__(self, p: orc.Params):
+        self.p = p.astype(np.float64)
+        self.C, self.D = p.C, p.D
+
+    def phase1(self, X, row_offset):
+        p, C = self.p, self.C
+        x = X.numpy().astype(np.float64)
+        N = x.shape[0]
+        cand = np.zeros(C * 131, np.float32)
+        idx = cand[:2 * C].view(np.int64)
+        if N == 0:
+            idx[:] = np.iinfo(np.int64).max
+            cand[2 * C:3 * C] = -np.inf
+            return torch.zeros(0, C), torch.zeros(0, 128, dtype=torch.float64), X.double(), torch.from_numpy(cand)
+        c = x @ p.Wi.T + p.bi
+        Q, _ = orc.q_mlp(x, p)
+        li = orc.critical_instances(c)
+        idx[:] = li + row_offset
+        cand[2 * C:3 * C] = c[li, np.arange(C)]
+        cand[3 * C:] = Q[li].reshape(-1)
+        return torch.from_numpy(c), torch.from_numpy(Q), torch.from_numpy(x), torch.from_numpy(cand)
+
+    def merge_candidates(self, cands, G):
+        C = self.C
+        recs = cands.numpy().reshape(G, C * 131)
+        qmax = np.zeros((C, 128), np.float32)
+        crit = np.zeros(C, np.int64)
+        for k in range(C):
+            best = None
+            for g in range(G):
+                gi = recs[g, :2 * C].view(np.int64)[k]
+                if gi == np.iinfo(np.int64).max:
+                    continue
+                key = (-recs[g, 2 * C + k], gi, g)
+                if best is None or key < best:
+                    best = key
+            crit[k] = best[1]
+            qmax[k] = recs[best[2], 3 * C + k * 128: 3 * C + (k + 1) * 128]
+        return torch.from_numpy(qmax), torch.from_numpy(crit)
+
+    def phase2(self, Vv, Q, qmax):
+        C, D = self.C, self.D
+        rec = np.zeros(C * (2 + D), np.float32)
+        if Q.shape[0] == 0:
+            rec[:C] = -np.inf
+            return torch.zeros(0, C, dtype=torch.float64), torch.from_numpy(rec)
+        L = (Q.numpy() @ qmax.numpy().astype(np.float64).T) / orc.SCALE_F32
+        m = L.max(0)
+        e = np.exp(L - m)
+        rec[:C], rec[C:2 * C] = m, e.sum(0)
+        rec[2 * C:] = (e.T @ Vv.numpy()).reshape(-1)
+        return torch.from_numpy(L), torch.from_numpy(rec)
+
+    def merge_partials(self, recs, G):
+        C, D = self.C, self.D
+        r = recs.numpy().reshape(G, C * (2 + D)).astype(np.float64)
+        m, s, Bp = r[:, :C], r[:, C:2 * C], r[:, 2 * C:].reshape(G, C, D)
+        M = m.max(0)
+        w = np.where(np.isinf(m), 0.0, np.exp(m - M))
+        out = np.concatenate([M, (s * w).sum(0), (Bp * w[:, :, None]).sum(0).reshape(-1)]).astype(np.float32)
+        return torch.from_numpy(out)
+
+    def phase3(self, rec, A):
+        C, D, p = self.C, self.D, self.p
+        r = rec.numpy().astype(np.float64)
+        M, S, Bm = r[:C], r[C:2 * C], r[2 * C:].reshape(C, D) / r[C:2 * C, None]
+        pred = p.Wf.reshape(C, -1) @ Bm.reshape(-1) + p.bf
+        An = np.exp(A.numpy() - M) / S if A.shape[0] else A.numpy()
+        return torch.from_numpy(An), torch.from_numpy(Bm.reshape(1, C, D)), torch.from_numpy(pred.reshape(1, C))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, name, N_override, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dsmil_wsi_b200.sharded import shard_bounds, sharded_forward
+        g, p, X = load_golden(name)
+        if N_override is not None:
+            X = X[:N_override]
+        lo, hi = shard_bounds(X.shape[0], world)[rank]
+        ops = OracleShardOps(p)
+        classes, pred, A, B, crit = sharded_forward(ops, torch.from_numpy(X[lo:hi]), lo, group=None)
+        ret[rank] = dict(lo=lo, hi=hi, classes=classes.numpy(), pred=pred.numpy(), A=A.numpy(), B=B.numpy(),
+                         crit=crit.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,name,N_override", [(2, "shipped_tcga", None), (2, "musk_d166_n7", None),
+                                                   (3, "lin_d512_c3", None), (2, "musk_d166_n7", 1)])
+def test_sharded_forward_over_gloo(world, name, N_override):
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, name, N_override, ret), nprocs=world, join=True)
+    g, p, X = load_golden(name)
+    if N_override is not None:
+        X = X[:N_override]
+    one = orc.forward(X, p)
+    for r in range(world):
+        o = ret[r]
+        assert np.array_equal(o["crit"], one.idx)                        # replicated, identical on all ranks
+        assert rel_to_max(o["pred"], one.prediction_bag) < 2e-6
+        assert rel_to_max(o["B"], one.B) < 2e-6
+        if o["hi"] > o["lo"]:
+            assert rel_to_max(o["classes"], one.classes[o["lo"]:o["hi"]]) < 1e-12
+            assert rel_to_max(o["A"], one.A[o["lo"]:o["hi"]]) < 2e-6      # records travel as fp32
+    assert sum(ret[r]["hi"] - ret[r]["lo"] for r in range(world)) == X.shape[0]
+
+
+def test_shard_bounds_cover_and_balance():
+    from dsmil_wsi_b200.sharded import shard_bounds
+    for N, G in [(10, 3), (7, 8), (100000, 8), (0, 2)]:
+        b = shard_bounds(N, G)
+        assert b[0][0] == 0 and b[-1][1] == N and all(b[i][1] == b[i + 1][0] for i in range(G - 1))
+        sizes = [hi - lo for lo, hi in b]
+        assert max(sizes) - min(sizes) <= 1
+    assert shard_bounds(10, 3) == list(orc.shard_bounds(10, 3))
