@@ -107,8 +107,9 @@ k_argmax(const float* __restrict__ classes, int64_t N, int C, unsigned long long
   }
 }
 
-// Candidate record layout (floats): idx[C] as int64 (2 floats each) | score[C] | qrow[C*128]
-__host__ __device__ inline size_t cand_floats(int C) { return static_cast<size_t>(C) * (2 + 1 + kQ); }
+// Candidate record layout (floats): idx[C] as int64 (2 floats each) | score[C] | qrow[C*128],
+// padded to a multiple of 4 floats so that records packed back to back keep the int64 aligned.
+__host__ __device__ inline size_t cand_floats(int C) { return (static_cast<size_t>(C) * (2 + 1 + kQ) + 3) & ~size_t(3); }
 
 __global__ void __launch_bounds__(128)
 k_gather_cand(const unsigned long long* __restrict__ keys, const float* __restrict__ classes,
@@ -162,8 +163,8 @@ k_merge_cand(const float* __restrict__ cands, int G, int C, float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// Partial record layout (floats): m[C] | s[C] | Bp[C*Dv]
-__host__ __device__ inline size_t rec_floats(int C, int Dv) { return static_cast<size_t>(C) * (2 + Dv); }
+// Partial record layout (floats): m[C] | s[C] | Bp[C*Dv], padded to a multiple of 4 floats
+__host__ __device__ inline size_t rec_floats(int C, int Dv) { return (static_cast<size_t>(C) * (2 + Dv) + 3) & ~size_t(3); }
 
 constexpr int kAttendRows = 32;
 

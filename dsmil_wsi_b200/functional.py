@@ -105,8 +105,7 @@ class MILForwardFn(torch.autograd.Function):
         if classes_in is not None:
             require_cuda(classes_in, "classes")
             cin = _f32c(classes_in.reshape(N, Cc))
-        need_grad = torch.is_grad_enabled() and any(
-            t is not None and t.requires_grad for t in (feats, Wi, bi, W1, b1, W2, b2, Wv, bv, Wf, bf))
+        need_grad = any(ctx.needs_input_grad)  # (grad mode is already off inside Function.forward)
         with torch.cuda.device(X.device):
             new = lambda *s: torch.empty(*s, dtype=torch.float32, device=X.device)
             classes = new(N, Cc) if cin is None else new(0, Cc)  # bag form: scores are an input, not an output

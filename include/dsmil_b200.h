@@ -129,9 +129,9 @@ int dsmil_backward(const dsmil_params_t* p, const float* X, const float* x_for_v
 /* ---- row-sharded forward (one giant bag over G ranks) -----------
  * Each rank owns rows [row_offset, row_offset+N_local).  Two exchange steps (all-gather of a
  * few KB, done by the caller with NCCL between the phases):
- *   phase1 -> cand record   [dsmil_cand_floats(C)]  = score[C] | idx[C] (int64 bits) | qrow[C,128]
+ *   phase1 -> cand record   [dsmil_cand_floats(C)]  = idx[C] (int64 bits) | score[C] | qrow[C,128] | pad to 4
  *   merge_candidates(G records) -> q_max[C,128], crit_idx[C]
- *   phase2 -> partial record [dsmil_rec_floats(C,Dv)] = m[C] | s[C] | Bpartial[C,Dv]
+ *   phase2 -> partial record [dsmil_rec_floats(C,Dv)] = m[C] | s[C] | Bpartial[C,Dv] | pad to 4
  *   merge_partials(G records)  -> global record
  *   phase3 -> A (normalised, local rows), B[1,C,Dv], pred[1,C] (replicated)
  * N_local may be 0 on a rank.  dsmil_forward == these five calls with G == 1. */

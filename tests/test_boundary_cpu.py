@@ -112,8 +112,8 @@ def test_library_exports_every_declared_symbol():
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
     assert lib.dsmil_abi_version() == 1
     # pure-host helpers are callable without a GPU
-    assert lib.dsmil_cand_floats(2) == 2 * (2 + 1 + 128)
-    assert lib.dsmil_rec_floats(2, 512) == 2 * (2 + 512)
+    assert lib.dsmil_cand_floats(2) == 264 and lib.dsmil_cand_floats(1) == 132   # 131*C padded to 4 floats
+    assert lib.dsmil_rec_floats(2, 512) == 2 * (2 + 512) and lib.dsmil_rec_floats(1, 166) == 168
     P = _lib.DsmilParams(512, 2, 1, 0)
     assert lib.dsmil_forward_workspace_bytes(ctypes.byref(P), 10000) > 2 * 10000 * 128 * 4
     assert lib.dsmil_backward_workspace_bytes(ctypes.byref(P), 10000, 0) > 0

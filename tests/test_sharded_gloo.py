@@ -21,12 +21,14 @@ class OracleShardOps:
     def __init__(self, p: orc.Params):
         self.p = p.astype(np.float64)
         self.C, self.D = p.C, p.D
+        self.cf = (p.C * 131 + 3) // 4 * 4          # records are padded to 4 floats (include/dsmil_b200.h)
+        self.rf = (p.C * (2 + p.D) + 3) // 4 * 4
 
     def phase1(self, X, row_offset):
         p, C = self.p, self.C
         x = X.numpy().astype(np.float64)
         N = x.shape[0]
-        cand = np.zeros(C * 131, np.float32)
+        cand = np.zeros(self.cf, np.float32)
         idx = cand[:2 * C].view(np.int64)
         if N == 0:
             idx[:] = np.iinfo(np.int64).max
@@ -37,12 +39,12 @@ class OracleShardOps:
         li = orc.critical_instances(c)
         idx[:] = li + row_offset
         cand[2 * C:3 * C] = c[li, np.arange(C)]
-        cand[3 * C:] = Q[li].reshape(-1)
+        cand[3 * C:3 * C + C * 128] = Q[li].reshape(-1)
         return torch.from_numpy(c), torch.from_numpy(Q), torch.from_numpy(x), torch.from_numpy(cand)
 
     def merge_candidates(self, cands, G):
         C = self.C
-        recs = cands.numpy().reshape(G, C * 131)
+        recs = cands.numpy().reshape(G, self.cf)
         qmax = np.zeros((C, 128), np.float32)
         crit = np.zeros(C, np.int64)
         for k in range(C):
@@ -60,7 +62,7 @@ class OracleShardOps:
 
     def phase2(self, Vv, Q, qmax):
         C, D = self.C, self.D
-        rec = np.zeros(C * (2 + D), np.float32)
+        rec = np.zeros(self.rf, np.float32)
         if Q.shape[0] == 0:
             rec[:C] = -np.inf
             return torch.zeros(0, C, dtype=torch.float64), torch.from_numpy(rec)
@@ -68,22 +70,23 @@ class OracleShardOps:
         m = L.max(0)
         e = np.exp(L - m)
         rec[:C], rec[C:2 * C] = m, e.sum(0)
-        rec[2 * C:] = (e.T @ Vv.numpy()).reshape(-1)
+        rec[2 * C:2 * C + C * D] = (e.T @ Vv.numpy()).reshape(-1)
         return torch.from_numpy(L), torch.from_numpy(rec)
 
     def merge_partials(self, recs, G):
         C, D = self.C, self.D
-        r = recs.numpy().reshape(G, C * (2 + D)).astype(np.float64)
-        m, s, Bp = r[:, :C], r[:, C:2 * C], r[:, 2 * C:].reshape(G, C, D)
+        r = recs.numpy().reshape(G, self.rf).astype(np.float64)
+        m, s, Bp = r[:, :C], r[:, C:2 * C], r[:, 2 * C:2 * C + C * D].reshape(G, C, D)
         M = m.max(0)
         w = np.where(np.isinf(m), 0.0, np.exp(m - M))
-        out = np.concatenate([M, (s * w).sum(0), (Bp * w[:, :, None]).sum(0).reshape(-1)]).astype(np.float32)
+        out = np.zeros(self.rf, np.float32)
+        out[:2 * C + C * D] = np.concatenate([M, (s * w).sum(0), (Bp * w[:, :, None]).sum(0).reshape(-1)])
         return torch.from_numpy(out)
 
     def phase3(self, rec, A):
         C, D, p = self.C, self.D, self.p
         r = rec.numpy().astype(np.float64)
-        M, S, Bm = r[:C], r[C:2 * C], r[2 * C:].reshape(C, D) / r[C:2 * C, None]
+        M, S, Bm = r[:C], r[C:2 * C], r[2 * C:2 * C + C * D].reshape(C, D) / r[C:2 * C, None]
         pred = p.Wf.reshape(C, -1) @ Bm.reshape(-1) + p.bf
         An = np.exp(A.numpy() - M) / S if A.shape[0] else A.numpy()
         return torch.from_numpy(An), torch.from_numpy(Bm.reshape(1, C, D)), torch.from_numpy(pred.reshape(1, C))
