@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 #include <algorithm>
 
@@ -12,6 +13,7 @@
 #include "gemm_generic.cuh"
 #include "fwd_kernels.cuh"
 #include "bwd_kernels.cuh"
+#include "fwd_sm100.cuh"
 
 namespace dsmil {
 
@@ -72,6 +74,7 @@ struct FwdWs {
   unsigned long long* keys;
   float *Q, *H1, *V, *cand, *qmax, *recs, *rec;
   int64_t* crit;
+  uint8_t* wimg;
   size_t bytes;
 };
 static FwdWs carve_fwd(const dsmil_params_t* p, int64_t N, void* ws, size_t cap, bool* ok) {
@@ -87,18 +90,75 @@ static FwdWs carve_fwd(const dsmil_params_t* p, int64_t N, void* ws, size_t cap,
   w.crit = c.take<int64_t>(kMaxC);
   w.recs = c.take<float>(static_cast<size_t>(attend_ctas(N)) * rec_floats(p->C, p->D));
   w.rec = c.take<float>(rec_floats(p->C, p->D));
+  w.wimg = sm100::qmlp_supported(p) ? c.take<uint8_t>(sm100::wimg_bytes(p->D) + 1024) : nullptr;
   w.bytes = c.off;
   *ok = c.ok();
   return w;
 }
 
 // ---- phase 1: scores + arg-max key + Q-MLP (+V) + candidate record --------------------------
+
+static int launch_scores(const dsmil_params_t* p, const float* X, int64_t N, float* classes,
+                         unsigned long long* keys, cudaStream_t st) {
+  const int C = p->C, D = p->D;
+  const size_t smem = sizeof(float) * C * D;
+  const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  const int mode = !vec ? 0 : (D % 64 == 0 ? 2 : 1);
+  const int grid = static_cast<int>(std::min<int64_t>(ceil_div(N, mode == 2 ? 16 : 8), 148 * 8));
+  prof_begin(PROF_SCORES, st);
+  if (mode == 2) {
+    if (smem > 48 * 1024) DSMIL_CUDA_OK(cudaFuncSetAttribute(k_scores<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_scores<2><<<grid, 256, smem, st>>>(X, N, D, p->Wi, p->bi, C, classes, keys);
+  } else if (mode == 1) {
+    if (smem > 48 * 1024) DSMIL_CUDA_OK(cudaFuncSetAttribute(k_scores<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_scores<1><<<grid, 256, smem, st>>>(X, N, D, p->Wi, p->bi, C, classes, keys);
+  } else {
+    if (smem > 48 * 1024) DSMIL_CUDA_OK(cudaFuncSetAttribute(k_scores<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_scores<0><<<grid, 256, smem, st>>>(X, N, D, p->Wi, p->bi, C, classes, keys);
+  }
+  prof_end(PROF_SCORES, st);
+  DSMIL_LAUNCH_OK("k_scores");
+  return 0;
+}
+
+static int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+static bool use_sm100(const dsmil_params_t* p) {
+  static int disabled = -1;
+  if (disabled < 0) { const char* e = getenv("DSMIL_B200_GENERIC"); disabled = (e && e[0] == '1') ? 1 : 0; }
+  return !disabled && sm100::qmlp_supported(p);
+}
+
 static int phase1_impl(const dsmil_params_t* p, const float* X, const float* xv, const float* classes_in,
                        int64_t N, int64_t row_offset, float* classes, float* Q, float* H1, float* V,
-                       float* cand, unsigned long long* keys, cudaStream_t st) {
+                       float* cand, unsigned long long* keys, uint8_t* wimg, cudaStream_t st) {
   const int C = p->C, D = p->D;
   DSMIL_CUDA_OK(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * kMaxC, st));
-  if (N > 0) {
+  if (N > 0 && use_sm100(p) && wimg && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+    // tensor-core path: scores + arg-max + Q-MLP in one persistent kernel
+    int rc;
+    if (classes_in) {
+      if (classes && classes != classes_in)
+        DSMIL_CUDA_OK(cudaMemcpyAsync(classes, classes_in, sizeof(float) * N * C, cudaMemcpyDeviceToDevice, st));
+      const int grid = static_cast<int>(std::min<int64_t>(ceil_div(N, 256), 296));
+      k_argmax<<<grid, 256, 0, st>>>(classes_in, N, C, keys);
+      DSMIL_LAUNCH_OK("k_argmax");
+    }
+    uint8_t* img = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wimg) + 1023) & ~uintptr_t(1023));
+    if ((rc = sm100::launch_qmlp(p, X, N, classes_in ? nullptr : classes, keys, Q, H1, img, num_sms(), st))) return rc;
+    if (p->passing_v) {
+      if ((rc = launch_linear<ACT_RELU, false>(xv ? xv : X, N, D, p->Wv, p->bv, D, V, nullptr, 0, st))) return rc;
+    }
+  } else if (N > 0) {
     if (classes_in) {
       if (classes && classes != classes_in)
         DSMIL_CUDA_OK(cudaMemcpyAsync(classes, classes_in, sizeof(float) * N * C, cudaMemcpyDeviceToDevice, st));
@@ -106,21 +166,8 @@ static int phase1_impl(const dsmil_params_t* p, const float* X, const float* xv,
       k_argmax<<<grid, 256, 0, st>>>(classes_in, N, C, keys);
       DSMIL_LAUNCH_OK("k_argmax");
     } else {
-      const size_t smem = sizeof(float) * C * D;
-      const int grid = static_cast<int>(std::min<int64_t>(ceil_div(N, 8), 148 * 8));
-      const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
-      prof_begin(PROF_SCORES, st);
-      if (vec) {
-        if (smem > 48 * 1024)
-          DSMIL_CUDA_OK(cudaFuncSetAttribute(k_scores<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_scores<true><<<grid, 256, smem, st>>>(X, N, D, p->Wi, p->bi, C, classes, keys);
-      } else {
-        if (smem > 48 * 1024)
-          DSMIL_CUDA_OK(cudaFuncSetAttribute(k_scores<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_scores<false><<<grid, 256, smem, st>>>(X, N, D, p->Wi, p->bi, C, classes, keys);
-      }
-      prof_end(PROF_SCORES, st);
-      DSMIL_LAUNCH_OK("k_scores");
+      int rcs = launch_scores(p, X, N, classes, keys, st);
+      if (rcs) return rcs;
     }
     int rc;
     prof_begin(PROF_QMLP, st);
@@ -217,7 +264,7 @@ static int forward_impl(const dsmil_params_t* p, const float* X, const float* xv
   float* Q = save_Q ? save_Q : w.Q;
   float* H1 = p->nonlinear ? (save_H1 ? save_H1 : w.H1) : nullptr;
   float* V = p->passing_v ? (save_V ? save_V : w.V) : nullptr;
-  if ((rc = phase1_impl(p, X, xv, classes_in, N, 0, classes, Q, H1, V, w.cand, w.keys, st))) return rc;
+  if ((rc = phase1_impl(p, X, xv, classes_in, N, 0, classes, Q, H1, V, w.cand, w.keys, w.wimg, st))) return rc;
   int64_t* crit = crit_idx ? crit_idx : w.crit;
   k_merge_cand<<<p->C, kQ, 0, st>>>(w.cand, 1, p->C, w.qmax, crit);
   DSMIL_LAUNCH_OK("k_merge_cand");
@@ -236,8 +283,8 @@ int dsmil_abi_version(void) { return DSMIL_ABI_VERSION; }
 const char* dsmil_last_error(void) { return g_err; }
 uint64_t dsmil_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int dsmil_forward_path(const dsmil_params_t* p, int64_t N) {
-  (void)p; (void)N;
-  return 1;
+  (void)N;
+  return (p && p->C >= 1 && p->C <= DSMIL_MAX_C && p->D >= 1 && p->D <= DSMIL_MAX_D && use_sm100(p)) ? 2 : 1;
 }
 
 int dsmil_profile_enable(int on) {
@@ -296,21 +343,7 @@ int dsmil_instance_scores(const dsmil_params_t* p, const float* X, int64_t N, fl
   // The arg-max by-product goes to a scratch key slot that is simply ignored here.
   unsigned long long* keys;
   DSMIL_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&keys), scratch_keys));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t smem = sizeof(float) * p->C * p->D;
-  const int grid = static_cast<int>(std::min<int64_t>(ceil_div(N, 8), 148 * 8));
-  const bool vec = (p->D % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
-  if (vec) {
-    if (smem > 48 * 1024)
-      DSMIL_CUDA_OK(cudaFuncSetAttribute(k_scores<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_scores<true><<<grid, 256, smem, st>>>(X, N, p->D, p->Wi, p->bi, p->C, classes, keys);
-  } else {
-    if (smem > 48 * 1024)
-      DSMIL_CUDA_OK(cudaFuncSetAttribute(k_scores<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_scores<false><<<grid, 256, smem, st>>>(X, N, p->D, p->Wi, p->bi, p->C, classes, keys);
-  }
-  DSMIL_LAUNCH_OK("k_scores");
-  return 0;
+  return launch_scores(p, X, N, classes, keys, static_cast<cudaStream_t>(stream));
 }
 
 // ---- sharded phases -----------------------------------------------------------------------
@@ -329,7 +362,7 @@ int dsmil_shard_phase1(const dsmil_params_t* p, const float* X, const float* x_f
     return DSMIL_ERR_WORKSPACE;
   }
   float* h1 = p->nonlinear ? (H1 ? H1 : w.H1) : nullptr;
-  return phase1_impl(p, X, x_for_v, classes_in, N_local, row_offset, classes, Q, h1, V, cand_rec, w.keys,
+  return phase1_impl(p, X, x_for_v, classes_in, N_local, row_offset, classes, Q, h1, V, cand_rec, w.keys, w.wimg,
                      static_cast<cudaStream_t>(stream));
 }
 

@@ -13,7 +13,11 @@ namespace dsmil {
 
 // ------------------------------------------------------------------------------------------
 // scores: one warp per row (grid-stride), Wi staged in shared memory, float4 loads when legal.
-template <bool VEC>
+// MODE 0: scalar loads (any D).  MODE 1: float4, one warp per row.  MODE 2 (D % 64 == 0): float4, HALF a
+// warp per row with exactly the summation order of the tensor-core kernel's fused scores
+// (fwd_sm100.cuh: lane `seg` takes float4 #seg of every 64-float chunk, then xor-shuffles 8,4,2,1), so
+// FCLayer/IClassifier scores are bit-identical whichever kernel produced them.
+template <int MODE>
 __global__ void __launch_bounds__(256)
 k_scores(const float* __restrict__ X, int64_t N, int D, const float* __restrict__ Wi,
          const float* __restrict__ bi, int C, float* __restrict__ classes,
@@ -26,16 +30,22 @@ k_scores(const float* __restrict__ X, int64_t N, int D, const float* __restrict_
   unsigned long long best[kMaxC];
 #pragma unroll
   for (int k = 0; k < kMaxC; ++k) best[k] = 0ull;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * 8;
-  for (int64_t n = static_cast<int64_t>(blockIdx.x) * 8 + warp; n < N; n += stride) {
+  constexpr int RPW = (MODE == 2) ? 2 : 1;  // rows per warp per iteration
+  const int sub = (MODE == 2) ? (lane >> 4) : 0;
+  const int seg = (MODE == 2) ? (lane & 15) : lane;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * 8 * RPW;
+  for (int64_t n0 = (static_cast<int64_t>(blockIdx.x) * 8 + warp) * RPW; n0 < N; n0 += stride) {
+    const int64_t n = n0 + sub;
+    const bool live = n < N;
     float acc[kMaxC];
 #pragma unroll
     for (int k = 0; k < kMaxC; ++k) acc[k] = 0.f;
-    const float* row = X + n * D;
-    if (VEC) {
+    const float* row = X + (live ? n : n0) * D;
+    if (MODE >= 1) {
       const float4* r4 = reinterpret_cast<const float4*>(row);
       const int D4 = D >> 2;
-      for (int j = lane; j < D4; j += 32) {
+      const int step = (MODE == 2) ? 16 : 32;
+      for (int j = seg; j < D4; j += step) {
         const float4 x = __ldg(r4 + j);
 #pragma unroll
         for (int k = 0; k < kMaxC; ++k)
@@ -58,17 +68,27 @@ k_scores(const float* __restrict__ X, int64_t N, int D, const float* __restrict_
 #pragma unroll
     for (int k = 0; k < kMaxC; ++k)
       if (k < C) {
-        const float v = warp_sum(acc[k]) + __ldg(bi + k);
-        if (lane == 0) {
+        float v = acc[k];
+        if (MODE == 2) {
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+        } else {
+          v = warp_sum(v);
+        }
+        v += __ldg(bi + k);
+        if (seg == 0 && live) {
           classes[n * C + k] = v;
           const unsigned long long key = pack_key(v, static_cast<uint32_t>(n));
           best[k] = key > best[k] ? key : best[k];
         }
       }
   }
-  if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < kMaxC; ++k) sbest[warp][k] = best[k];
+  for (int k = 0; k < kMaxC; ++k) {
+    best[k] = warp_max_u64(best[k]);   // MODE 2 keeps two partial bests per warp (lanes 0 and 16)
+    if (lane == 0) sbest[warp][k] = best[k];
   }
   __syncthreads();
   if (threadIdx.x < C) {

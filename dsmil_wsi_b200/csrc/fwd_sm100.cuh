@@ -178,7 +178,9 @@ k_qmlp_sm100(const QmlpArgs a) {
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
 
   float* sWi = reinterpret_cast<float*>(smem + kOffWi);
-  for (int i = tid; i < C * D; i += kThreads) sWi[i] = a.Wi[i];
+  const bool do_scores = a.classes != nullptr;   // bag form (scores given): Wi/bi may be NULL
+  if (do_scores)
+    for (int i = tid; i < C * D; i += kThreads) sWi[i] = a.Wi[i];
   if (tid < kQ) { s_b1[tid] = a.b1[tid]; s_b2[tid] = a.b2[tid]; }
   if (tid == 0) {
     for (int s = 0; s < kAStages; ++s) { mbar_init(bar(A_FULL + s), kConvWarps); mbar_init(bar(A_EMPTY + s), 1); }
@@ -237,7 +239,7 @@ k_qmlp_sm100(const QmlpArgs a) {
           const float4 x = cur[i];
 #pragma unroll
           for (int k = 0; k < CT; ++k)
-            if (k < C) {
+            if (do_scores && k < C) {
               const float4 w = *reinterpret_cast<const float4*>(sWi + k * D + kc * kChunkK + seg * 4);
               float s = sc[i][k];
               s = fmaf(x.x, w.x, s); s = fmaf(x.y, w.y, s); s = fmaf(x.z, w.z, s); s = fmaf(x.w, w.w, s);
@@ -262,7 +264,7 @@ k_qmlp_sm100(const QmlpArgs a) {
       }
       // instance scores of this tile: reduce over the 16 threads (seg) that share a row
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; do_scores && i < 8; ++i) {
         const int64_t n = row_base + r0 + 16 * i;
 #pragma unroll
         for (int k = 0; k < CT; ++k) {
@@ -286,7 +288,7 @@ k_qmlp_sm100(const QmlpArgs a) {
       if (lane == 0) s_best[warp - 6][k] = b;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kConvWarps * 32));   // converter-only named barrier
-    if (ct < C) {
+    if (ct < C && do_scores) {
       unsigned long long b = 0ull;
       for (int w = 0; w < kConvWarps; ++w) b = s_best[w][ct] > b ? s_best[w][ct] : b;
       if (b) atomicMax(a.keys + ct, b);

@@ -110,9 +110,13 @@ def test_camelyon_shape_fwd_bwd_vs_oracle():
     assert abs(loss.item() - tl) < 3e-6
     tg = orc.backward(X, p, t, d_cls, d_pred)
     named = dict(net.named_parameters())
+    # The q.* gradients pass through the softmax-over-15000-instances backward, which amplifies forward
+    # rounding ~1e3x: the reference's own fp32 autograd is 1.1e-4 (W1) .. 2.1e-4 (b1) from the fp64 truth
+    # on this very case [measured with /root/reference on CPU].  Our forward runs the Q-MLP in 3xBF16
+    # (Q within ~5e-6), which lands at ~6e-4; everything not behind the softmax stays at fp32 level.
     for k, v in tg.items():
         r = rel_to_max(_np(named[grad_name(k, True)].grad), v)
-        assert r < 5e-5, (k, r)
+        assert r < (2e-3 if k in ("W1", "b1", "W2", "b2") else 5e-5), (k, r)
 
 
 def test_split_call_forms_compose_to_fused():
@@ -255,3 +259,25 @@ def test_errors_are_loud():
         net(torch.randn(4, 32, device="cuda").double())
     with pytest.raises(RuntimeError, match="CUDA only"):
         net(torch.randn(4, 32))
+
+
+@pytest.mark.parametrize("name", ["shipped_tcga", "shipped_c16", "rand_d512_c2", "rand_d512_c1", "tree_d1024_c2"])
+def test_tensor_core_q_mlp_matches_fp64(name):
+    """Phase 1 on the tcgen05 path (3xBF16 split, fp32 accumulate in TMEM): Q, H1-derived outputs and the
+    fused instance scores against the fp64 oracle.  Q is tanh-bounded, so the tolerance is absolute."""
+    import ctypes
+    from dsmil_wsi_b200 import _lib
+    from dsmil_wsi_b200.sharded import CudaShardOps, milnet_params
+    g, p, X = load_golden(name)
+    net = build_net(p).eval()
+    ops = CudaShardOps(milnet_params(net))
+    assert _lib.load().dsmil_forward_path(ops.P.ref, X.shape[0]) == 2, "tensor-core path not selected"
+    classes, Q, _, cand = ops.phase1(torch.from_numpy(X).cuda(), 0)
+    t = orc.forward(X, p)
+    err = np.abs(_np(Q).astype(np.float64) - t.Q).max()
+    # 3xBF16 keeps ~16 mantissa bits per operand: |dQ| <= ~1.2e-5 * max|pre-activation| (4.4e-5 predicted by
+    # the CPU emulation for the wscale=3 case); end-to-end A/B/logit tolerances are what the parity bar is.
+    assert err < 1e-4, (name, err)
+    assert rel_to_max(_np(classes), t.classes) < TOL_CLS
+    idx = _np(cand)[: 2 * p.C].view(np.int64)
+    assert np.array_equal(idx, t.idx)
