@@ -227,7 +227,7 @@ def run_ours(args):
     def step():
         with torch.no_grad():
             if world == 1:
-                return [net(b) for b in bags]
+                return net.forward_bags(bags)
             return sharded_forward_bags(ops, bags, offsets)
 
     def barrier():

@@ -14,6 +14,7 @@
 #include "fwd_kernels.cuh"
 #include "bwd_kernels.cuh"
 #include "fwd_sm100.cuh"
+#include "fwd_batched.cuh"
 
 namespace dsmil {
 
@@ -32,6 +33,8 @@ int cuda_fail(cudaError_t e, const char* what) {
   return DSMIL_ERR_CUDA;
 }
 void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+namespace sm100 { long long* g_trace_buf = nullptr; }
 
 // ---- live kernel timing ------------------------------------------------------------------
 bool g_prof_on = false;
@@ -90,7 +93,7 @@ static FwdWs carve_fwd(const dsmil_params_t* p, int64_t N, void* ws, size_t cap,
   w.crit = c.take<int64_t>(kMaxC);
   w.recs = c.take<float>(static_cast<size_t>(attend_ctas(N)) * rec_floats(p->C, p->D));
   w.rec = c.take<float>(rec_floats(p->C, p->D));
-  w.wimg = sm100::qmlp_supported(p) ? c.take<uint8_t>(sm100::wimg_bytes(p->D) + 1024) : nullptr;
+  w.wimg = sm100::qmlp_supported(p) ? c.take<uint8_t>(sm100::wimg_bytes(p->D) + 1024 + 256) : nullptr;
   w.bytes = c.off;
   *ok = c.ok();
   return w;
@@ -154,7 +157,13 @@ static int phase1_impl(const dsmil_params_t* p, const float* X, const float* xv,
       DSMIL_LAUNCH_OK("k_argmax");
     }
     uint8_t* img = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wimg) + 1023) & ~uintptr_t(1023));
-    if ((rc = sm100::launch_qmlp(p, X, N, classes_in ? nullptr : classes, keys, Q, H1, img, num_sms(), st))) return rc;
+    sm100::BagDev* tbl = reinterpret_cast<sm100::BagDev*>(img + sm100::wimg_bytes(D));
+    sm100::BagDev one{X, N, 0, 0, 0, 1, 0};
+    DSMIL_CUDA_OK(cudaMemcpyAsync(tbl, &one, sizeof(one), cudaMemcpyHostToDevice, st));
+    if ((rc = sm100::launch_prep_wimg(p, img, st))) return rc;
+    const int ntiles = static_cast<int>((N + sm100::kTileM - 1) / sm100::kTileM);
+    if ((rc = sm100::launch_qmlp(p, tbl, 0, 1, 0, ntiles, classes_in ? nullptr : classes, keys, Q, H1, img, num_sms(), st)))
+      return rc;
     if (p->passing_v) {
       if ((rc = launch_linear<ACT_RELU, false>(xv ? xv : X, N, D, p->Wv, p->bv, D, V, nullptr, 0, st))) return rc;
     }
@@ -244,6 +253,11 @@ static int phase3_impl(const dsmil_params_t* p, int64_t N, const float* rec, flo
   return 0;
 }
 
+static int forward_bags_impl(const dsmil_params_t* p, const float* const* Xs, const int64_t* Ns, int nb,
+                             const float* classes_in, float* classes, float* pred, float* A, float* B,
+                             int64_t* crit, float* save_Q, float* save_H1, void* ws, size_t ws_bytes,
+                             cudaStream_t st);
+
 static int forward_impl(const dsmil_params_t* p, const float* X, const float* xv, const float* classes_in,
                         int64_t N, float* classes, float* pred, float* A, float* B, int64_t* crit_idx,
                         float* save_Q, float* save_H1, float* save_V, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -255,6 +269,8 @@ static int forward_impl(const dsmil_params_t* p, const float* X, const float* xv
     return DSMIL_ERR_EMPTY;
   }
   DSMIL_REQUIRE(X && pred && A && B && (classes || classes_in), "NULL tensor pointer");
+  if (use_sm100(p) && sm100::batched_supported(p) && (reinterpret_cast<uintptr_t>(X) & 15) == 0)
+    return forward_bags_impl(p, &X, &N, 1, classes_in, classes, pred, A, B, crit_idx, save_Q, save_H1, ws, ws_bytes, st);
   bool ok;
   FwdWs w = carve_fwd(p, N, ws, ws_bytes, &ok);
   if (!ws || !ok) {
@@ -273,6 +289,113 @@ static int forward_impl(const dsmil_params_t* p, const float* X, const float* xv
   return phase3_impl(p, N, w.rec, A, B, pred, st);
 }
 
+
+// ---- batched forward: a stream of bags in a handful of launches (tensor-core path only) -----------
+struct BagsWs {
+  sm100::BagDev* table;
+  unsigned long long* keys;
+  float* Q;
+  uint8_t* wimg;
+  float* recs;
+  float* pred_part;
+  unsigned int* counters;
+  size_t bytes;
+};
+static inline int recs_for_bag(int64_t N) {
+  const int64_t t = (N + sm100::kAttRows - 1) / sm100::kAttRows;
+  return static_cast<int>(t < sm100::kMaxRecPerBag ? (t < 1 ? 1 : t) : sm100::kMaxRecPerBag);
+}
+static BagsWs carve_bags(const dsmil_params_t* p, const int64_t* Ns, int nb, bool need_Q, void* ws, size_t cap,
+                         bool* ok) {
+  Carver c(ws, cap);
+  BagsWs w;
+  int64_t total = 0, nrec = 0;
+  for (int b = 0; b < nb; ++b) { total += Ns[b]; nrec += recs_for_bag(Ns[b]); }
+  w.table = c.take<sm100::BagDev>(nb);
+  // keys and the finalize arrival counters are zeroed together (one memset): keep them adjacent
+  w.keys = c.take<unsigned long long>(static_cast<size_t>(nb) * (kMaxC + 1));
+  w.counters = reinterpret_cast<unsigned int*>(w.keys ? w.keys + static_cast<size_t>(nb) * kMaxC : nullptr);
+  w.pred_part = c.take<float>(static_cast<size_t>(nb) * sm100::kFinSlices * kMaxC);
+  w.Q = need_Q ? c.take<float>(static_cast<size_t>(total) * kQ) : nullptr;
+  w.wimg = c.take<uint8_t>(sm100::wimg_bytes(p->D) + 1024);
+  w.recs = c.take<float>(static_cast<size_t>(nrec) * rec_floats(p->C, p->D));
+  w.bytes = c.off;
+  *ok = c.ok();
+  return w;
+}
+static size_t l2_budget_bytes() {
+  static size_t v = 0;
+  if (!v) {
+    const char* e = getenv("DSMIL_B200_L2_MB");
+    const long mb = e ? atol(e) : 72;
+    v = static_cast<size_t>(mb > 0 ? mb : 72) << 20;
+  }
+  return v;
+}
+
+static int forward_bags_impl(const dsmil_params_t* p, const float* const* Xs, const int64_t* Ns, int nb,
+                             const float* classes_in, float* classes, float* pred, float* A, float* B,
+                             int64_t* crit, float* save_Q, float* save_H1, void* ws, size_t ws_bytes,
+                             cudaStream_t st) {
+  const int C = p->C, D = p->D;
+  bool ok;
+  BagsWs w = carve_bags(p, Ns, nb, save_Q == nullptr, ws, ws_bytes, &ok);
+  if (!ws || !ok) {
+    set_error("workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes);
+    return DSMIL_ERR_WORKSPACE;
+  }
+  std::vector<sm100::BagDev> tbl(nb);
+  long long row = 0;
+  int tile = 0, rec = 0;
+  for (int b = 0; b < nb; ++b) {
+    DSMIL_REQUIRE(Ns[b] >= 1 && Ns[b] < 0xffffffffll && Xs[b], "bag %d: empty or NULL", b);
+    DSMIL_REQUIRE((reinterpret_cast<uintptr_t>(Xs[b]) & 15) == 0, "bag %d: features must be 16-byte aligned", b);
+    const int nrec = recs_for_bag(Ns[b]);
+    tbl[b] = sm100::BagDev{Xs[b], Ns[b], row, tile, rec, nrec, 0};
+    row += Ns[b];
+    tile += static_cast<int>((Ns[b] + sm100::kTileM - 1) / sm100::kTileM);
+    rec += nrec;
+  }
+  DSMIL_CUDA_OK(cudaMemcpyAsync(w.table, tbl.data(), sizeof(sm100::BagDev) * nb, cudaMemcpyHostToDevice, st));
+  DSMIL_CUDA_OK(cudaMemsetAsync(w.keys, 0, sizeof(unsigned long long) * (kMaxC + 1) * nb, st));
+  uint8_t* img = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(w.wimg) + 1023) & ~uintptr_t(1023));
+  int rc;
+  if ((rc = sm100::launch_prep_wimg(p, img, st))) return rc;
+  float* Q = save_Q ? save_Q : w.Q;
+  if (classes_in) {   // bag form: arg-max of the given scores (single bag only)
+    const int grid = static_cast<int>(std::min<int64_t>(ceil_div(Ns[0], 256), 296));
+    k_argmax<<<grid, 256, 0, st>>>(classes_in, Ns[0], C, w.keys);
+    DSMIL_LAUNCH_OK("k_argmax");
+  }
+  // sub-batches sized so that a sub-batch's features (+Q) are still in L2 when the attend pass re-reads them
+  const size_t budget = l2_budget_bytes();
+  int b0 = 0;
+  while (b0 < nb) {
+    int b1 = b0;
+    size_t bytes = 0;
+    while (b1 < nb) {
+      const size_t add = static_cast<size_t>(Ns[b1]) * (D + kQ) * sizeof(float);
+      if (b1 > b0 && bytes + add > budget) break;
+      bytes += add;
+      ++b1;
+    }
+    const int t0 = tbl[b0].tile_off;
+    const int t1 = (b1 < nb) ? tbl[b1].tile_off : tile;
+    const int r0 = tbl[b0].rec_off;
+    const int r1 = (b1 < nb) ? tbl[b1].rec_off : rec;
+    if ((rc = sm100::launch_qmlp(p, w.table, b0, b1 - b0, t0, t1 - t0, classes_in ? nullptr : classes, w.keys, Q,
+                                 save_H1, img, num_sms(), st)))
+      return rc;
+    sm100::AttendArgs aa{w.table, b0, b1 - b0, r0, D, C, Q, w.keys, A, w.recs};
+    if ((rc = sm100::launch_attend_b(aa, r1 - r0, st))) return rc;
+    sm100::FinalizeArgs fa{w.table, b0, D, C, w.recs, w.keys, p->Wf, p->bf, A, B, pred,
+                           reinterpret_cast<long long*>(crit), w.pred_part, w.counters};
+    if ((rc = sm100::launch_finalize_b(fa, b1 - b0, st))) return rc;
+    b0 = b1;
+  }
+  return 0;
+}
+
 }  // namespace dsmil
 
 using namespace dsmil;
@@ -285,6 +408,12 @@ uint64_t dsmil_launch_count(void) { return g_launches.load(std::memory_order_rel
 int dsmil_forward_path(const dsmil_params_t* p, int64_t N) {
   (void)N;
   return (p && p->C >= 1 && p->C <= DSMIL_MAX_C && p->D >= 1 && p->D <= DSMIL_MAX_D && use_sm100(p)) ? 2 : 1;
+}
+
+/* Debug: CTA-0 timeline of the tensor-core kernel (clock64 stamps).  buf = device int64[3*8*64] or NULL. */
+int dsmil_debug_set_trace(void* buf) {
+  sm100::g_trace_buf = static_cast<long long*>(buf);
+  return 0;
 }
 
 int dsmil_profile_enable(int on) {
@@ -313,7 +442,43 @@ size_t dsmil_rec_floats(int32_t C, int32_t Dv) { return rec_floats(C, Dv); }
 size_t dsmil_forward_workspace_bytes(const dsmil_params_t* p, int64_t N) {
   if (!p || p->C < 1 || p->C > DSMIL_MAX_C || p->D < 1 || p->D > DSMIL_MAX_D || N < 0) return 0;
   bool ok;
-  return carve_fwd(p, N, nullptr, 0, &ok).bytes;
+  size_t a = carve_fwd(p, N, nullptr, 0, &ok).bytes;
+  if (sm100::batched_supported(p) && N > 0) a = std::max(a, carve_bags(p, &N, 1, true, nullptr, 0, &ok).bytes);
+  return a;
+}
+
+size_t dsmil_forward_bags_workspace_bytes(const dsmil_params_t* p, const int64_t* Ns, int32_t nb) {
+  if (!p || !Ns || nb < 1 || p->C < 1 || p->C > DSMIL_MAX_C || p->D < 1 || p->D > DSMIL_MAX_D) return 0;
+  bool ok;
+  if (sm100::batched_supported(p)) return carve_bags(p, Ns, nb, true, nullptr, 0, &ok).bytes;
+  int64_t mx = 0;
+  for (int b = 0; b < nb; ++b) mx = std::max<int64_t>(mx, Ns[b]);
+  return carve_fwd(p, mx, nullptr, 0, &ok).bytes;
+}
+
+int dsmil_forward_bags(const dsmil_params_t* p, const float* const* Xs, const int64_t* Ns, int32_t nb,
+                       float* classes, float* pred, float* A, float* B, int64_t* crit_idx, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  int rc = check_params(p, true);
+  if (rc) return rc;
+  DSMIL_REQUIRE(Xs && Ns && nb >= 1 && classes && pred && A && B, "NULL pointer or nb < 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bool aligned = true;
+  for (int b = 0; b < nb; ++b) aligned = aligned && Xs[b] && (reinterpret_cast<uintptr_t>(Xs[b]) & 15) == 0 && Ns[b] >= 1;
+  if (use_sm100(p) && sm100::batched_supported(p) && aligned)
+    return forward_bags_impl(p, Xs, Ns, nb, nullptr, classes, pred, A, B, crit_idx, nullptr, nullptr, workspace,
+                             workspace_bytes, st);
+  // shapes the tensor-core kernels do not take: same packed outputs, one bag at a time
+  int64_t row = 0;
+  for (int b = 0; b < nb; ++b) {
+    rc = forward_impl(p, Xs[b], nullptr, nullptr, Ns[b], classes + row * p->C, pred + static_cast<size_t>(b) * p->C,
+                      A + row * p->C, B + static_cast<size_t>(b) * p->C * p->D,
+                      crit_idx ? crit_idx + static_cast<size_t>(b) * p->C : nullptr, nullptr, nullptr, nullptr,
+                      workspace, workspace_bytes, st);
+    if (rc) return rc;
+    row += Ns[b];
+  }
+  return 0;
 }
 size_t dsmil_shard_workspace_bytes(const dsmil_params_t* p, int64_t N_local) {
   return dsmil_forward_workspace_bytes(p, N_local);
@@ -361,7 +526,7 @@ int dsmil_shard_phase1(const dsmil_params_t* p, const float* X, const float* x_f
     set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
     return DSMIL_ERR_WORKSPACE;
   }
-  float* h1 = p->nonlinear ? (H1 ? H1 : w.H1) : nullptr;
+  float* h1 = p->nonlinear ? (H1 ? H1 : (use_sm100(p) ? nullptr : w.H1)) : nullptr;   // tc path keeps H1 in TMEM
   return phase1_impl(p, X, x_for_v, classes_in, N_local, row_offset, classes, Q, h1, V, cand_rec, w.keys, w.wimg,
                      static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,356 @@
+// Batched (bag-table) phase 2/3 kernels used with the tensor-core phase 1 (fwd_sm100.cuh).
+//   k_attend_b     dsmil.py:53-57  per (bag, CTA): q_max = Q[critical rows], logits -> A (unnormalised),
+//                                  online softmax over the instance axis, partial bag vector
+//   k_finalize_b   dsmil.py:56-61  per bag: combine partial records, normalise A, B, Conv1d bag logits,
+//                                  critical indices
+// Requirements: D % 4 == 0, D <= 2048, feature rows 16-byte aligned, identity V.
+#pragma once
+#include "common.cuh"
+#include "fwd_kernels.cuh"
+#include "fwd_sm100.cuh"
+
+namespace dsmil {
+namespace sm100 {
+
+constexpr int kAttRows = 128;          // rows per attend tile (same tiling as phase 1)
+constexpr int kMaxRecPerBag = 128;
+
+struct AttendArgs {
+  const BagDev* bags;
+  int bag0, nb;
+  int rec0;                 // first record index covered by this launch (== blockIdx.x 0)
+  int D, C;
+  const float* Q;           // packed [sumN,128]
+  const unsigned long long* keys;  // [nbags][kMaxC]
+  float* A;                 // packed [sumN,C]: receives the raw logits here
+  float* recs;              // [total records][rec_floats(C,D)]
+};
+
+// CT = classes rounded up to 1,2,4; NJ = float4 column groups per thread (D <= 512*NJ)
+template <int CT, int NJ>
+__global__ void __launch_bounds__(256)
+k_attend_b(const AttendArgs a) {
+  extern __shared__ __align__(16) float s_dyn[];           // [C][D] cross-half reduction buffer
+  __shared__ __align__(16) float sq[CT][kQ];
+  __shared__ float sL[kAttRows][CT];
+  __shared__ float sE[kAttRows][CT];
+  __shared__ float s_red[8][CT];
+  __shared__ float s_m[CT], s_s[CT], s_scale[CT];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = a.C, D = a.D;
+  // which bag does this CTA belong to?
+  const int rec = a.rec0 + blockIdx.x;
+  int bag = a.bag0;
+  while (bag < a.bag0 + a.nb - 1 && rec >= a.bags[bag + 1].rec_off) ++bag;
+  const BagDev bg = a.bags[bag];
+  const int cta_in_bag = rec - bg.rec_off;
+  const int ntiles = static_cast<int>((bg.N + kAttRows - 1) / kAttRows);
+
+  // q_max rows (dsmil.py:53-54: the critical instances' queries; here gathered from Q, same bits)
+  for (int i = tid; i < CT * kQ; i += 256) {
+    const int k = i / kQ, j = i % kQ;
+    float v = 0.f;
+    if (k < C) {
+      const long long row = key_row(a.keys[static_cast<size_t>(bag) * kMaxC + k]);
+      v = a.Q[(bg.row_off + row) * kQ + j];
+    }
+    sq[k][j] = v;
+  }
+  if (tid < CT) { s_m[tid] = -INFINITY; s_s[tid] = 0.f; }
+  float acc[CT][NJ][4];
+#pragma unroll
+  for (int k = 0; k < CT; ++k)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[k][j][e] = 0.f;
+  __syncthreads();
+
+  const int half = tid >> 7, c4 = tid & 127;     // row parity handled / float4 column within a 512-float span
+  const int D4 = D >> 2;
+  for (int t = cta_in_bag; t < ntiles; t += bg.nrec) {
+    const long long r0 = static_cast<long long>(t) * kAttRows;
+    const int rows = static_cast<int>((bg.N - r0) < kAttRows ? (bg.N - r0) : kAttRows);
+    // (a) logits: warp w owns rows w*16 .. w*16+15
+#pragma unroll 4
+    for (int rr = 0; rr < 16; ++rr) {
+      const int r = warp * 16 + rr;
+      if (r < rows) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(a.Q + (bg.row_off + r0 + r) * kQ) + lane);
+#pragma unroll
+        for (int k = 0; k < CT; ++k) {
+          const float4 w = *reinterpret_cast<const float4*>(&sq[k][lane * 4]);
+          float d = q.x * w.x;
+          d = fmaf(q.y, w.y, d);
+          d = fmaf(q.z, w.z, d);
+          d = fmaf(q.w, w.w, d);
+          d = warp_sum(d);
+          if (lane == 0) {
+            const float L = __fdiv_rn(d, kScale);   // dsmil.py:56: a division by sqrt(128f)
+            sL[r][k] = L;
+            if (k < C) a.A[(bg.row_off + r0 + r) * C + k] = L;
+          }
+        }
+      } else if (lane < CT) {
+        sL[r][lane] = -INFINITY;
+      }
+    }
+    __syncthreads();
+    // (b) running max, rescale factor, exp weights, running sum
+    if (tid < CT) {
+      float mx = s_m[tid];
+      for (int r = 0; r < kAttRows; ++r) mx = fmaxf(mx, sL[r][tid]);
+      const float old = s_m[tid];
+      s_scale[tid] = (old == -INFINITY) ? 0.f : expf(old - mx);
+      s_m[tid] = mx;
+    }
+    __syncthreads();
+    {
+      float e[CT];
+#pragma unroll
+      for (int k = 0; k < CT; ++k) {
+        float ev = 0.f;
+        if (tid < kAttRows) {
+          const float L = sL[tid][k];
+          ev = (L == -INFINITY) ? 0.f : expf(L - s_m[k]);
+          sE[tid][k] = ev;
+        }
+        e[k] = warp_sum(ev);
+        if (lane == 0) s_red[warp][k] = e[k];
+      }
+    }
+    __syncthreads();
+    if (tid < CT) {
+      float s = s_s[tid] * s_scale[tid];
+      for (int w = 0; w < 4; ++w) s += s_red[w][tid];    // rows live in threads 0..127 == warps 0..3
+      s_s[tid] = s;
+    }
+    // (c) weighted feature sum: this thread takes rows of its parity, float4 columns c4 + 128*j
+#pragma unroll
+    for (int k = 0; k < CT; ++k) {
+      const float sc = s_scale[k];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[k][j][e] *= sc;
+    }
+    const float* xb = bg.X + r0 * D;
+#pragma unroll 4
+    for (int r = half; r < rows; r += 2) {
+      float4 x[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int col = c4 + 128 * j;
+        x[j] = col < D4 ? __ldg(reinterpret_cast<const float4*>(xb + static_cast<long long>(r) * D) + col)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < CT; ++k) {
+        const float e = sE[r][k];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          acc[k][j][0] = fmaf(e, x[j].x, acc[k][j][0]);
+          acc[k][j][1] = fmaf(e, x[j].y, acc[k][j][1]);
+          acc[k][j][2] = fmaf(e, x[j].z, acc[k][j][2]);
+          acc[k][j][3] = fmaf(e, x[j].w, acc[k][j][3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // fold the two row parities (fixed order: even rows + odd rows) and emit the record
+  float* recp = a.recs + static_cast<size_t>(rec) * rec_floats(C, D);
+  if (half == 1) {
+#pragma unroll
+    for (int k = 0; k < CT; ++k)
+      if (k < C)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int col = c4 + 128 * j;
+          if (col < D4)
+            *reinterpret_cast<float4*>(s_dyn + k * D + col * 4) =
+                make_float4(acc[k][j][0], acc[k][j][1], acc[k][j][2], acc[k][j][3]);
+        }
+  }
+  __syncthreads();
+  if (half == 0) {
+#pragma unroll
+    for (int k = 0; k < CT; ++k)
+      if (k < C)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int col = c4 + 128 * j;
+          if (col < D4) {
+            const float4 o = *reinterpret_cast<const float4*>(s_dyn + k * D + col * 4);
+            float* dst = recp + 2 * C + static_cast<size_t>(k) * D + col * 4;
+            dst[0] = acc[k][j][0] + o.x;
+            dst[1] = acc[k][j][1] + o.y;
+            dst[2] = acc[k][j][2] + o.z;
+            dst[3] = acc[k][j][3] + o.w;
+          }
+        }
+  }
+  if (tid < C) { recp[tid] = s_m[tid]; recp[C + tid] = s_s[tid]; }
+}
+
+struct FinalizeArgs {
+  const BagDev* bags;
+  int bag0;
+  int D, C;
+  const float* recs;
+  const unsigned long long* keys;
+  const float* Wf;
+  const float* bf;
+  float* A;       // packed, logits in / softmax out
+  float* B;       // [nbags, C, D]
+  float* pred;    // [nbags, C]
+  long long* crit;  // [nbags, C] or NULL
+  float* pred_part;        // [nbags][kFinSlices][kMaxC] partial bag logits
+  unsigned int* counters;  // [nbags] arrival counters (zeroed by the host before the batch)
+};
+
+constexpr int kFinSlices = 8;
+
+// grid = (kFinSlices, nb).  Every CTA derives (M, S) of its bag from the <=128 partial records, normalises
+// its share of A, combines its share of the B columns (records summed in a fixed interleaved order ->
+// deterministic) and contributes a partial Conv1d dot product; the last CTA of the bag to finish adds the
+// kFinSlices partials in slice order (dsmil.py:59-61) and writes the critical indices.
+__global__ void __launch_bounds__(256)
+k_finalize_b(const FinalizeArgs a) {
+  __shared__ float sw[kMaxRecPerBag][kMaxC];
+  __shared__ float sM[kMaxC], sS[kMaxC];
+  __shared__ float s_part[256];
+  __shared__ float red[8][kMaxC];
+  __shared__ unsigned int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = a.C, D = a.D;
+  const int bag = a.bag0 + blockIdx.y;
+  const BagDev bg = a.bags[bag];
+  const size_t rstride = rec_floats(C, D);
+  const float* recs = a.recs + static_cast<size_t>(bg.rec_off) * rstride;
+  const int P = bg.nrec;
+  // (M, S): thread (k, j) scans records j, j+32, ... ; fixed-order combine
+  for (int k = warp; k < C; k += 8) {
+    float m = -INFINITY;
+    for (int p = lane; p < P; p += 32) m = fmaxf(m, recs[p * rstride + k]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int p = lane; p < P; p += 32) {
+      const float mp = recs[p * rstride + k];
+      const float w = (mp == -INFINITY) ? 0.f : expf(mp - m);
+      sw[p][k] = w;
+      s = fmaf(recs[p * rstride + C + k], w, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) { sM[k] = m; sS[k] = s; }
+  }
+  __syncthreads();
+  {  // normalise this slice's rows of A
+    const long long total = bg.N * C;
+    const long long per = (total + gridDim.x - 1) / gridDim.x;
+    const long long lo = per * blockIdx.x, hi = (lo + per) < total ? (lo + per) : total;
+    float* Ab = a.A + bg.row_off * C;
+    for (long long i = lo + tid; i < hi; i += 256) {
+      const int k = static_cast<int>(i % C);
+      Ab[i] = __fdiv_rn(expf(Ab[i] - sM[k]), sS[k]);
+    }
+  }
+  // B columns of this slice: element e = k*D + d; two threads per element split the records (even / odd)
+  const int CD = C * D;
+  const int eps = (CD + kFinSlices - 1) / kFinSlices;
+  const int e_lo = eps * blockIdx.x, e_hi = (e_lo + eps) < CD ? (e_lo + eps) : CD;
+  float ppart[kMaxC];
+#pragma unroll
+  for (int k = 0; k < kMaxC; ++k) ppart[k] = 0.f;
+  for (int base = e_lo; base < e_hi; base += 128) {
+    const int e = base + (tid & 127);
+    const int par = tid >> 7;
+    float acc = 0.f;
+    if (e < e_hi) {
+      const int k = e / D;
+      const float* col = recs + 2 * C + e;
+      int p = par;
+#pragma unroll 1
+      for (; p + 14 < P; p += 16) {   // 8 independent loads in flight
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = col[static_cast<size_t>(p + 2 * u) * rstride];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fmaf(v[u], sw[p + 2 * u][k], acc);
+      }
+      for (; p < P; p += 2) acc = fmaf(col[static_cast<size_t>(p) * rstride], sw[p][k], acc);
+    }
+    if (par == 1) s_part[tid & 127] = acc;
+    __syncthreads();
+    if (par == 0 && e < e_hi) {
+      const int k = e / D;
+      const float b = __fdiv_rn(acc + s_part[tid], sS[k]);
+      a.B[static_cast<size_t>(bag) * CD + e] = b;
+      for (int kk = 0; kk < C; ++kk) ppart[kk] = fmaf(__ldg(a.Wf + static_cast<size_t>(kk) * CD + e), b, ppart[kk]);
+    }
+    __syncthreads();
+  }
+  // partial Conv1d logits of this slice (fixed reduction order inside the CTA)
+  for (int kk = 0; kk < C; ++kk) {
+    const float v = warp_sum(ppart[kk]);
+    if (lane == 0) red[warp][kk] = v;
+  }
+  __syncthreads();
+  float* part = a.pred_part + (static_cast<size_t>(bag) * kFinSlices + blockIdx.x) * kMaxC;
+  if (tid < C) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][tid];
+    part[tid] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(a.counters + bag, 1u);
+  __syncthreads();
+  if (s_last != kFinSlices - 1) return;
+  __threadfence();
+  if (tid < C) {
+    const volatile float* pp = a.pred_part + static_cast<size_t>(bag) * kFinSlices * kMaxC;
+    float s = 0.f;
+    for (int sl = 0; sl < kFinSlices; ++sl) s += pp[sl * kMaxC + tid];
+    a.pred[static_cast<size_t>(bag) * C + tid] = s + __ldg(a.bf + tid);
+    if (a.crit) a.crit[static_cast<size_t>(bag) * C + tid] = key_row(a.keys[static_cast<size_t>(bag) * kMaxC + tid]);
+  }
+}
+
+inline bool batched_supported(const dsmil_params_t* p) {
+  return qmlp_supported(p) && !p->passing_v && p->D % 4 == 0 && p->D <= 2048 && p->C <= 4 &&
+         ((p->C <= 2) || p->D <= 1024);
+}
+
+inline int launch_attend_b(const AttendArgs& a, int nrecs, cudaStream_t st) {
+  const int C = a.C, D = a.D;
+  const size_t smem = sizeof(float) * C * D;
+  const int NJ = D <= 512 ? 1 : (D <= 1024 ? 2 : 4);
+  auto go = [&](auto kern) -> int {
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+      DSMIL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      configured = smem;
+    }
+    prof_begin(PROF_ATTEND, st);
+    kern<<<nrecs, 256, smem, st>>>(a);
+    prof_end(PROF_ATTEND, st);
+    DSMIL_LAUNCH_OK("k_attend_b");
+    return 0;
+  };
+  if (C == 1) { if (NJ == 1) return go(k_attend_b<1, 1>); if (NJ == 2) return go(k_attend_b<1, 2>); return go(k_attend_b<1, 4>); }
+  if (C == 2) { if (NJ == 1) return go(k_attend_b<2, 1>); if (NJ == 2) return go(k_attend_b<2, 2>); return go(k_attend_b<2, 4>); }
+  if (NJ == 1) return go(k_attend_b<4, 1>);
+  return go(k_attend_b<4, 2>);
+}
+
+inline int launch_finalize_b(const FinalizeArgs& a, int nb, cudaStream_t st) {
+  prof_begin(PROF_FINAL, st);
+  k_finalize_b<<<dim3(kFinSlices, nb), 256, 0, st>>>(a);
+  prof_end(PROF_FINAL, st);
+  DSMIL_LAUNCH_OK("k_finalize_b");
+  return 0;
+}
+
+}  // namespace sm100
+}  // namespace dsmil

@@ -15,6 +15,8 @@
 //   TMEM columns (512): H1 accumulators 2 x 128 | Q accumulator 128 | A2 hi 64 | A2 lo 64
 #pragma once
 #include <cuda_bf16.h>
+#include <type_traits>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -28,7 +30,21 @@ constexpr int kChunkBytes = 2 * kTileBytes;            // hi tile + lo tile
 constexpr int kAStages = 2;
 constexpr int kWStages = 2;
 constexpr int kConvWarps = 8;
-constexpr int kThreads = 32 * (4 + 1 + 1 + kConvWarps);  // epilogue x4, MMA, TMA, converters
+constexpr int kEpiWarps = 8;             // two warps per TMEM lane quadrant, each takes 64 of the 128 columns
+// Roles are aligned to warpgroups (4 warps) so that setmaxnreg can move registers between them:
+// WG0-1 epilogue | WG2-3 converters | WG4 = MMA issuer, W producer, 2 idle warps
+constexpr int kWarpConv0 = kEpiWarps, kWarpMma = kEpiWarps + kConvWarps, kWarpTma = kWarpMma + 1;
+constexpr int kThreads = 32 * (kEpiWarps + kConvWarps + 4);
+// The pool is what the CTA got at launch: 96 regs x 640 threads = 61440 (an .inc blocks until .dec frees enough)
+constexpr int kRegsConv = 136, kRegsEpi = 88, kRegsCtl = 32;   // 256*136 + 256*88 + 128*32 = 61440
+template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {   // read-once data: keep it out of L1
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 constexpr uint32_t kSpinLimit = 1u << 28;
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -42,7 +58,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t sleep_ns = 0) {
   uint32_t done = 0, spins = 0;
   while (true) {
     asm volatile(
@@ -51,6 +67,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) break;
+    if (sleep_ns) __nanosleep(sleep_ns);
     if (++spins > kSpinLimit) __trap();  // a protocol bug must not hang the GPU
   }
 }
@@ -94,6 +111,17 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t bde
                ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),  \
                  "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]),          \
                  "r"(v[14]), "r"(v[15]) : "memory")
+#define DSMIL_TMEM_LD16(taddr, v)                                                                          \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                   \
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                            \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),       \
+                 "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),   \
+                 "=r"(v[14]), "=r"(v[15])                                                                  \
+               : "r"(taddr) : "memory")
+#define DSMIL_TMEM_ST8(taddr, v)                                                                           \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"                    \
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),  \
+                 "r"(v[7]) : "memory")
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -104,9 +132,26 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return static_cast<uint64_t>((saddr & 0x3ffffu) >> 4) | (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
          (1ull << 46) | (2ull << 61);
 }
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// The same descriptor as two 32-bit words: only the low word (start address) changes between MMAs.
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3ffffu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void mma_ss2(uint32_t d, uint32_t alo, uint32_t blo, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %3, 0;\n\t"
+      "mov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d), "r"(alo), "r"(blo), "r"(acc), "r"(kDescHi), "r"(kIdesc) : "memory");
+}
+__device__ __forceinline__ void mma_ts2(uint32_t d, uint32_t a_tmem, uint32_t blo, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %3, 0;\n\t"
+      "mov.b64 db, {%2, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %5, p;\n\t}"
+      ::"r"(d), "r"(a_tmem), "r"(blo), "r"(acc), "r"(kDescHi), "r"(kIdesc) : "memory");
+}
 // kind::f16 instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, both K-major,
 // N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
 // byte offset of element (row, k) inside one [rows x 64] bf16 SWIZZLE_128B tile
 __host__ __device__ inline uint32_t swz_off(int row, int k) {
@@ -130,28 +175,71 @@ k_prep_wimg(const float* __restrict__ W, int K, uint8_t* __restrict__ img) {
   }
 }
 
+// One bag of a batch, as the kernels see it (device memory, built by the host per call).
+struct BagDev {
+  const float* X;       // [N, D]
+  long long N;
+  long long row_off;    // first row of this bag in the packed outputs (classes, A, Q, H1)
+  int tile_off;         // first 128-row tile of this bag in the batch-wide tile numbering
+  int rec_off;          // first partial record of this bag
+  int nrec;             // partial records (== attend CTAs) of this bag
+  int pad_;
+};
+
+extern long long* g_trace_buf;   // device buffer (3*8*64 int64) or NULL
+inline int debug_mode() {
+  static int m = -1;
+  if (m < 0) { const char* e = getenv("DSMIL_B200_DEBUG_MODE"); m = e ? atoi(e) : 0; }
+  return m;
+}
+
 struct QmlpArgs {
-  const float* X;
-  int64_t N;
-  int D;
-  int C;
+  const BagDev* bags;
+  int bag0, nb;           // bags [bag0, bag0+nb) are covered by this launch ...
+  int tile0, ntiles;      // ... which are tiles [tile0, tile0+ntiles)
+  int D, C;
   const float* Wi;
   const float* bi;
   const float* b1;
   const float* b2;
   const uint8_t* w1img;   // D/64 chunks
   const uint8_t* w2img;   // 2 chunks
-  float* classes;         // [N,C]
-  unsigned long long* keys;
-  float* Q;               // [N,128]
-  float* H1;              // [N,128] or NULL
+  float* classes;         // packed [sumN, C] or NULL (scores given by the caller)
+  unsigned long long* keys;  // [nbags][kMaxC]
+  float* Q;               // packed [sumN,128]
+  float* H1;              // packed [sumN,128] or NULL
+  long long* dbg;         // optional timeline of CTA 0 (clock64 stamps), see DSMIL_B200_TRACE in abi.cu
+  int mode;               // timing experiments only (DSMIL_B200_DEBUG_MODE): bit0 no Q stores, bit1 no scores,
+                          // bit2 converter skips convert+store, bit3 no MMAs, bit4 epilogue skips math
 };
+// trace slots: [role][event][index] -> role 0 converter (warp 0 of the role), 1 mma, 2 epilogue
+#define DSMIL_TRACE(role, ev, idx)                                                            \
+  do {                                                                                        \
+    if (a.dbg != nullptr && blockIdx.x == 0 && (idx) < 64)                                    \
+      a.dbg[((role) * 8 + (ev)) * 64 + (idx)] = clock64();                                    \
+  } while (0)
+
+// Walks the bag table as a role's tile index increases monotonically.
+struct TileCursor {
+  const BagDev* bags;
+  int bag, last;
+  __device__ TileCursor(const BagDev* b, int bag0, int nb) : bags(b), bag(bag0), last(bag0 + nb - 1) {}
+  __device__ __forceinline__ void seek(int tile) {
+    while (bag < last && tile >= bags[bag + 1].tile_off) ++bag;
+  }
+};
+
+__device__ __forceinline__ float fast_tanh(float x) {
+  // tanh(x) = 1 - 2/(exp(2x)+1); ex2.approx + rcp.approx: |err| < ~3e-7 absolute, saturates correctly
+  const float e = __expf(2.f * x);
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
 
 // dynamic smem carve (bytes, from a 1024-aligned base)
 constexpr int kOffW2 = 0;                                   // 2 chunks x 32 KiB
 constexpr int kOffWRing = kOffW2 + 2 * kChunkBytes;         // kWStages x 32 KiB
 constexpr int kOffARing = kOffWRing + kWStages * kChunkBytes;
-constexpr int kOffWi = kOffARing + kAStages * kChunkBytes;  // up to 8 x 2048 floats?  (C*D floats)
+constexpr int kOffWi = kOffARing + kAStages * kChunkBytes;  // C*D floats
 constexpr int kSmemFixed = kOffWi;
 
 template <int CT>
@@ -162,13 +250,12 @@ k_qmlp_sm100(const QmlpArgs a) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t bars[32];
   __shared__ uint32_t s_tmem_base;
-  __shared__ float s_b1[kQ], s_b2[kQ];
-  __shared__ unsigned long long s_best[kConvWarps][kMaxC];
+  __shared__ __align__(16) float s_b1[kQ], s_b2[kQ];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = a.D, C = a.C;
   const int nchunks = D / kChunkK;
-  const int64_t ntiles = (a.N + kTileM - 1) / kTileM;
+  const int tile_end = a.tile0 + a.ntiles;
 
   // barrier indices
   enum { A_FULL = 0, A_EMPTY = A_FULL + kAStages, W_FULL = A_EMPTY + kAStages, W_EMPTY = W_FULL + kWStages,
@@ -178,20 +265,20 @@ k_qmlp_sm100(const QmlpArgs a) {
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
 
   float* sWi = reinterpret_cast<float*>(smem + kOffWi);
-  const bool do_scores = a.classes != nullptr;   // bag form (scores given): Wi/bi may be NULL
+  const bool do_scores = a.classes != nullptr && !(a.mode & 2);   // bag form (scores given): Wi/bi may be NULL
   if (do_scores)
     for (int i = tid; i < C * D; i += kThreads) sWi[i] = a.Wi[i];
   if (tid < kQ) { s_b1[tid] = a.b1[tid]; s_b2[tid] = a.b2[tid]; }
   if (tid == 0) {
     for (int s = 0; s < kAStages; ++s) { mbar_init(bar(A_FULL + s), kConvWarps); mbar_init(bar(A_EMPTY + s), 1); }
     for (int s = 0; s < kWStages; ++s) { mbar_init(bar(W_FULL + s), 1); mbar_init(bar(W_EMPTY + s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar(H1_FULL + b), 1); mbar_init(bar(H1_EMPTY + b), 128); }
-    mbar_init(bar(A2_FULL), 128); mbar_init(bar(A2_EMPTY), 1);
-    mbar_init(bar(Q_FULL), 1); mbar_init(bar(Q_EMPTY), 128);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar(H1_FULL + b), 1); mbar_init(bar(H1_EMPTY + b), kEpiWarps * 32); }
+    mbar_init(bar(A2_FULL), kEpiWarps * 32); mbar_init(bar(A2_EMPTY), 1);
+    mbar_init(bar(Q_FULL), 1); mbar_init(bar(Q_EMPTY), kEpiWarps * 32);
     mbar_init(bar(W2_FULL), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {  // TMEM allocation (whole 512 columns; one CTA per SM by construction)
+  if (warp == kWarpMma) {  // TMEM allocation (whole 512 columns; one CTA per SM by construction)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(smem_u32(&s_tmem_base)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -199,158 +286,208 @@ k_qmlp_sm100(const QmlpArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (tid == 0) DSMIL_TRACE(2, 7, 0);   // prologue done
   const uint32_t tmem = s_tmem_base;
-  const uint32_t tm_h1[2] = {tmem + 0, tmem + 128};
+  const uint32_t tm_h1_0 = tmem, tm_h1_1 = tmem + 128;
   const uint32_t tm_q = tmem + 256, tm_a2hi = tmem + 384, tm_a2lo = tmem + 448;
 
-  if (warp >= 6) {
+  if (warp >= kWarpConv0 && warp < kWarpMma) {
     // =============================== converter warps =========================================
-    const int ct = tid - 6 * 32;                 // 0..255
+    reg_inc<kRegsConv>();
+    const int ct = tid - kWarpConv0 * 32;        // 0..255
     const int seg = ct & 15, r0 = ct >> 4;       // float4 index in the 64-float chunk row; base row
-    unsigned long long best[CT];
-#pragma unroll
-    for (int k = 0; k < CT; ++k) best[k] = 0ull;
     uint32_t stage = 0, phase = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t row_base = tile * kTileM;
+    TileCursor cur_bag(a.bags, a.bag0, a.nb);
+    for (int tile = a.tile0 + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+      cur_bag.seek(tile);
+      const BagDev bg = a.bags[cur_bag.bag];
+      const long long row_base = static_cast<long long>(tile - bg.tile_off) * kTileM;   // row inside the bag
       float sc[8][CT];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int k = 0; k < CT; ++k) sc[i][k] = 0.f;
-      float4 cur[8], nxt[8];
-      auto load_chunk = [&](int kc, float4* dst) {
+      const bool full = row_base + kTileM <= bg.N;
+      const float4* xrow = reinterpret_cast<const float4*>(bg.X + (row_base + r0) * D) + seg;
+      const long long rstride4 = 4ll * D;          // 16 rows, in float4 units
+      // Half-chunk h = (k-chunk h>>1, row half h&1): 4 float4 per thread.  Four register buffers, loads are
+      // issued three half-chunks (48 KB per SM) ahead of their use to cover the HBM latency.
+      auto load_half = [&](int h, float4* dst) {
+        const int kc = h >> 1, part = h & 1;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t n = row_base + r0 + 16 * i;
-          dst[i] = (n < a.N) ? __ldg(reinterpret_cast<const float4*>(a.X + n * D + kc * kChunkK) + seg)
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i) {
+          const int ri = i + 4 * part;
+          const float4* src = xrow + ri * rstride4 + kc * (kChunkK / 4);
+          dst[i] = (full || row_base + r0 + 16 * ri < bg.N) ? ldg_stream(src) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
-      load_chunk(0, cur);
-      for (int kc = 0; kc < nchunks; ++kc) {
-        if (kc + 1 < nchunks) load_chunk(kc + 1, nxt);
-        mbar_wait(bar(A_EMPTY + stage), phase ^ 1);
-        uint8_t* hi_tile = smem + kOffARing + stage * kChunkBytes;
-        uint8_t* lo_tile = hi_tile + kTileBytes;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + 16 * i;
-          const float4 x = cur[i];
+      const uint32_t off0 = swz_off(r0, seg * 4);  // rows r0 + 16 i share (row & 7): offset_i = off0 + 2048 i
+      float4 wk[CT];
+      uint8_t* hi_tile = nullptr;
+      auto proc_half = [&](int h, const float4* src, auto part_c) {
+        constexpr int part = decltype(part_c)::value;
+        const int kc = h >> 1;
+        if (part == 0) {
 #pragma unroll
           for (int k = 0; k < CT; ++k)
-            if (do_scores && k < C) {
-              const float4 w = *reinterpret_cast<const float4*>(sWi + k * D + kc * kChunkK + seg * 4);
-              float s = sc[i][k];
-              s = fmaf(x.x, w.x, s); s = fmaf(x.y, w.y, s); s = fmaf(x.z, w.z, s); s = fmaf(x.w, w.w, s);
-              sc[i][k] = s;
-            }
+            wk[k] = (do_scores && k < C) ? *reinterpret_cast<const float4*>(sWi + k * D + kc * kChunkK + seg * 4)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ct == 0 && tile == a.tile0 + 2 * static_cast<int>(gridDim.x)) DSMIL_TRACE(0, 0, kc);   // chunk start
+          mbar_wait(bar(A_EMPTY + stage), phase ^ 1);
+          if (ct == 0 && tile == a.tile0 + 2 * static_cast<int>(gridDim.x)) DSMIL_TRACE(0, 1, kc);   // stage free
+          hi_tile = smem + kOffARing + stage * kChunkBytes + off0;
+        }
+        uint8_t* lo_tile = hi_tile + kTileBytes;
+        if (a.mode & 4) {   // experiment: consume the loads, no conversion
+          float t = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) t += src[i].x + src[i].w;
+          if (t == 123456.f) *reinterpret_cast<float*>(hi_tile) = t;
+        } else
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 x = src[i];
+          if (part == 0 && i == 0 && ct == 0 && tile == a.tile0 + 2 * static_cast<int>(gridDim.x)) { if (x.x == 123456.f) DSMIL_TRACE(0, 5, kc); DSMIL_TRACE(0, 2, kc); }
+#pragma unroll
+          for (int k = 0; k < CT; ++k) {
+            float s = sc[i + 4 * part][k];
+            s = fmaf(x.x, wk[k].x, s); s = fmaf(x.y, wk[k].y, s); s = fmaf(x.z, wk[k].z, s); s = fmaf(x.w, wk[k].w, s);
+            sc[i + 4 * part][k] = s;
+          }
           const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
           const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - __low2float(h01), x.y - __high2float(h01));
           const __nv_bfloat162 l23 = __floats2bfloat162_rn(x.z - __low2float(h23), x.w - __high2float(h23));
-          const uint32_t off = swz_off(r, seg * 4);
           uint2 hv, lv;
           hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
           lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-          *reinterpret_cast<uint2*>(hi_tile + off) = hv;
-          *reinterpret_cast<uint2*>(lo_tile + off) = lv;
+          *reinterpret_cast<uint2*>(hi_tile + (i + 4 * part) * 2048) = hv;
+          *reinterpret_cast<uint2*>(lo_tile + (i + 4 * part) * 2048) = lv;
         }
-        fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(A_FULL + stage));
-        if (++stage == kAStages) { stage = 0; phase ^= 1; }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+        if (part == 1) {
+          if (!(a.mode & 128)) fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(A_FULL + stage));
+          if (ct == 0 && tile == a.tile0 + 2 * static_cast<int>(gridDim.x)) DSMIL_TRACE(0, 3, kc);   // stage published
+          if (++stage == kAStages) { stage = 0; phase ^= 1; }
+        }
+      };
+      using P0 = std::integral_constant<int, 0>;
+      using P1 = std::integral_constant<int, 1>;
+      const int nh = 2 * nchunks;                  // multiple of 4 (D % 128 == 0)
+      float4 b0[4], b1[4], b2[4], b3[4];
+      load_half(0, b0); load_half(1, b1); load_half(2, b2);
+      for (int h = 0; h < nh; h += 4) {
+        load_half(h + 3, b3);
+        proc_half(h, b0, P0{});
+        if (h + 4 < nh) load_half(h + 4, b0);
+        proc_half(h + 1, b1, P1{});
+        if (h + 5 < nh) load_half(h + 5, b1);
+        proc_half(h + 2, b2, P0{});
+        if (h + 6 < nh) load_half(h + 6, b2);
+        proc_half(h + 3, b3, P1{});
       }
-      // instance scores of this tile: reduce over the 16 threads (seg) that share a row
+      // instance scores of this tile: reduce over the 16 threads (seg) that share a row; the per-class
+      // arg-max key of the tile goes straight to the bag's key slot (one atomicMax per warp and class)
+      if (do_scores) {
+        unsigned long long best[CT];
 #pragma unroll
-      for (int i = 0; do_scores && i < 8; ++i) {
-        const int64_t n = row_base + r0 + 16 * i;
+        for (int k = 0; k < CT; ++k) best[k] = 0ull;
 #pragma unroll
-        for (int k = 0; k < CT; ++k) {
-          float v = sc[i][k];
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          v += __shfl_xor_sync(0xffffffffu, v, 2);
-          v += __shfl_xor_sync(0xffffffffu, v, 1);
-          if (seg == 0 && k < C && n < a.N) {
-            v += a.bi[k];
-            a.classes[n * C + k] = v;
-            const unsigned long long key = pack_key(v, static_cast<uint32_t>(n));
-            best[k] = key > best[k] ? key : best[k];
+        for (int i = 0; i < 8; ++i) {
+          const long long n = row_base + r0 + 16 * i;
+#pragma unroll
+          for (int k = 0; k < CT; ++k) {
+            float v = sc[i][k];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            if (seg == 0 && k < C && n < bg.N) {
+              v += a.bi[k];
+              a.classes[(bg.row_off + n) * C + k] = v;
+              const unsigned long long key = pack_key(v, static_cast<uint32_t>(n));
+              best[k] = key > best[k] ? key : best[k];
+            }
           }
         }
+#pragma unroll
+        for (int k = 0; k < CT; ++k) {
+          const unsigned long long b = warp_max_u64(best[k]);
+          if (lane == 0 && k < C && b) atomicMax(a.keys + static_cast<size_t>(cur_bag.bag) * kMaxC + k, b);
+        }
       }
     }
-#pragma unroll
-    for (int k = 0; k < CT; ++k) {
-      const unsigned long long b = warp_max_u64(best[k]);
-      if (lane == 0) s_best[warp - 6][k] = b;
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kConvWarps * 32));   // converter-only named barrier
-    if (ct < C && do_scores) {
-      unsigned long long b = 0ull;
-      for (int w = 0; w < kConvWarps; ++w) b = s_best[w][ct] > b ? s_best[w][ct] : b;
-      if (b) atomicMax(a.keys + ct, b);
-    }
-  } else if (warp == 5) {
+  } else if (warp >= kWarpMma && warp != kWarpMma && warp != kWarpTma) {
+    reg_dec<kRegsCtl>();     // idle warps of the control warpgroup
+  } else if (warp == kWarpTma) {
     // =============================== W1 image producer (bulk copies) ==========================
+    reg_dec<kRegsCtl>();
     if (lane == 0) {
       mbar_expect_tx(bar(W2_FULL), 2 * kChunkBytes);
       bulk_g2s(smem_u32(smem + kOffW2), a.w2img, 2 * kChunkBytes, bar(W2_FULL));
       uint32_t stage = 0, phase = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = a.tile0 + blockIdx.x; tile < tile_end; tile += gridDim.x) {
         for (int kc = 0; kc < nchunks; ++kc) {
-          mbar_wait(bar(W_EMPTY + stage), phase ^ 1);
+          mbar_wait(bar(W_EMPTY + stage), phase ^ 1, (a.mode & 64) ? 100 : 0);
+          if ((a.mode & 32) && tile != a.tile0 + static_cast<int>(blockIdx.x)) {   // experiment: no W streaming
+            mbar_arrive(bar(W_FULL + stage));
+          } else {
           mbar_expect_tx(bar(W_FULL + stage), kChunkBytes);
           bulk_g2s(smem_u32(smem + kOffWRing + stage * kChunkBytes), a.w1img + static_cast<size_t>(kc) * kChunkBytes,
                    kChunkBytes, bar(W_FULL + stage));
+          }
           if (++stage == kWStages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kWarpMma) {
     // =============================== MMA issuer ================================================
+    reg_dec<kRegsCtl>();
     if (lane == 0) {
       uint32_t as = 0, aph = 0, ws = 0, wph = 0;
       const uint32_t w2base = smem_u32(smem + kOffW2);
-      auto issue_l2 = [&](int64_t j) {   // layer 2 of the j-th local tile: Qacc = A2(tmem) * W2^T
+      auto issue_l2 = [&](int j) {   // layer 2 of the j-th local tile: Qacc = A2(tmem) * W2^T
+        DSMIL_TRACE(1, 3, j);
         mbar_wait(bar(A2_FULL), j & 1);
+        DSMIL_TRACE(1, 4, j);
         mbar_wait(bar(Q_EMPTY), (j & 1) ^ 1);
+        DSMIL_TRACE(1, 5, j);
         tc_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t wb = w2base + (ks >> 2) * kChunkBytes + (ks & 3) * 32;
-          const uint64_t bhi = make_desc(wb), blo = make_desc(wb + kTileBytes);
-          mma_ts(tm_q, tm_a2hi + ks * 8, bhi, kIdesc, ks > 0);
-          mma_ts(tm_q, tm_a2lo + ks * 8, bhi, kIdesc, 1);
-          mma_ts(tm_q, tm_a2hi + ks * 8, blo, kIdesc, 1);
+        for (int ks = 0; ks < ((a.mode & 8) ? 0 : 8); ++ks) {
+          const uint32_t bhi = desc_lo(w2base + (ks >> 2) * kChunkBytes + (ks & 3) * 32);
+          const uint32_t blo = bhi + (kTileBytes >> 4);
+          mma_ts2(tm_q, tm_a2hi + ks * 8, bhi, ks > 0);
+          mma_ts2(tm_q, tm_a2lo + ks * 8, bhi, 1);
+          mma_ts2(tm_q, tm_a2hi + ks * 8, blo, 1);
         }
         tc_commit(bar(Q_FULL));
         tc_commit(bar(A2_EMPTY));
       };
       mbar_wait(bar(W2_FULL), 0);
-      int64_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      int it = 0;
+      for (int tile = a.tile0 + blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
         const int b = it & 1;
         mbar_wait(bar(H1_EMPTY + b), ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         for (int kc = 0; kc < nchunks; ++kc) {
           mbar_wait(bar(A_FULL + as), aph);
+          if (it == 2) DSMIL_TRACE(1, 0, kc);
           mbar_wait(bar(W_FULL + ws), wph);
+          if (it == 2) DSMIL_TRACE(1, 1, kc);
           tc_fence_after();
-          const uint32_t ab = smem_u32(smem + kOffARing + as * kChunkBytes);
-          const uint32_t wb = smem_u32(smem + kOffWRing + ws * kChunkBytes);
+          const uint32_t ab = desc_lo(smem_u32(smem + kOffARing + as * kChunkBytes));
+          const uint32_t wb = desc_lo(smem_u32(smem + kOffWRing + ws * kChunkBytes));
+          const uint32_t dacc = b ? tm_h1_1 : tm_h1_0;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ahi = make_desc(ab + ks * 32), alo = make_desc(ab + kTileBytes + ks * 32);
-            const uint64_t bhi = make_desc(wb + ks * 32), blo = make_desc(wb + kTileBytes + ks * 32);
-            mma_ss(tm_h1[b], ahi, bhi, kIdesc, (kc | ks) != 0);
-            mma_ss(tm_h1[b], alo, bhi, kIdesc, 1);
-            mma_ss(tm_h1[b], ahi, blo, kIdesc, 1);
+          for (int ks = 0; ks < ((a.mode & 8) ? 0 : 4); ++ks) {   // +32 B per K-step == +2 in descriptor units; lo tile is +1024 units
+            mma_ss2(dacc, ab + ks * 2, wb + ks * 2, (kc | ks) != 0);
+            mma_ss2(dacc, ab + (kTileBytes >> 4) + ks * 2, wb + ks * 2, 1);
+            mma_ss2(dacc, ab + ks * 2, wb + (kTileBytes >> 4) + ks * 2, 1);
           }
           tc_commit(bar(A_EMPTY + as));
           tc_commit(bar(W_EMPTY + ws));
+          if (it == 2) DSMIL_TRACE(1, 2, kc);
           if (++as == kAStages) { as = 0; aph ^= 1; }
           if (++ws == kWStages) { ws = 0; wph ^= 1; }
         }
@@ -360,50 +497,66 @@ k_qmlp_sm100(const QmlpArgs a) {
       if (it > 0) issue_l2(it - 1);
     }
   } else {
-    // =============================== epilogue warps (TMEM lane quadrant = warp) ===============
-    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
-    const int row_in_tile = warp * 32 + lane;
-    auto q_epilogue = [&](int64_t j, int64_t tile) {
-      mbar_wait(bar(Q_FULL), j & 1);
+    // ====== epilogue warps: TMEM lane quadrant = warp & 3, column half = warp >> 2 =============
+    reg_dec<kRegsEpi>();
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int row_in_tile = (warp & 3) * 32 + lane;
+    const int col0 = (warp >> 2) * 64;
+    auto q_epilogue = [&](int j, long long grow, bool live) {   // grow: packed row index of this thread's row
+      mbar_wait(bar(Q_FULL), j & 1, (a.mode & 64) ? 200 : 0);
       tc_fence_after();
-      const int64_t n = tile * kTileM + row_in_tile;
 #pragma unroll 1
-      for (int c0 = 0; c0 < kQ; c0 += 32) {
-        uint32_t v[32];
-        DSMIL_TMEM_LD32(tm_q + lane_sel + c0, v);
+      for (int c0 = col0; c0 < col0 + 64; c0 += 16) {
+        uint32_t v[16];
+        DSMIL_TMEM_LD16(tm_q + lane_sel + c0, v);
         tmem_wait_ld();
-        if (c0 == kQ - 32) { tc_fence_before(); mbar_arrive(bar(Q_EMPTY)); }
-        if (n < a.N) {
-          float4* dst = reinterpret_cast<float4*>(a.Q + n * kQ + c0);
+        if (c0 == col0 + 48) { tc_fence_before(); mbar_arrive(bar(Q_EMPTY)); }
+        if (live && !(a.mode & 16)) {
+          float4* dst = reinterpret_cast<float4*>((a.mode & 1) ? a.Q + (threadIdx.x & 255) * 4 : a.Q + grow * kQ + c0);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < 4; ++q) {
+            const float4 bb = *reinterpret_cast<const float4*>(&s_b2[c0 + 4 * q]);
             float4 o;
-            o.x = tanhf(__uint_as_float(v[4 * q + 0]) + s_b2[c0 + 4 * q + 0]);
-            o.y = tanhf(__uint_as_float(v[4 * q + 1]) + s_b2[c0 + 4 * q + 1]);
-            o.z = tanhf(__uint_as_float(v[4 * q + 2]) + s_b2[c0 + 4 * q + 2]);
-            o.w = tanhf(__uint_as_float(v[4 * q + 3]) + s_b2[c0 + 4 * q + 3]);
+            o.x = fast_tanh(__uint_as_float(v[4 * q + 0]) + bb.x);
+            o.y = fast_tanh(__uint_as_float(v[4 * q + 1]) + bb.y);
+            o.z = fast_tanh(__uint_as_float(v[4 * q + 2]) + bb.z);
+            o.w = fast_tanh(__uint_as_float(v[4 * q + 3]) + bb.w);
             dst[q] = o;
           }
         }
       }
     };
-    int64_t it = 0, prev_tile = -1;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    int it = 0;
+    long long prev_grow = 0;
+    bool prev_live = false;
+    TileCursor cur_bag(a.bags, a.bag0, a.nb);
+    for (int tile = a.tile0 + blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
+      cur_bag.seek(tile);
+      const BagDev bg = a.bags[cur_bag.bag];
+      const long long n = static_cast<long long>(tile - bg.tile_off) * kTileM + row_in_tile;
+      const bool live = n < bg.N;
+      const long long grow = bg.row_off + n;
       const int b = it & 1;
-      const int64_t n = tile * kTileM + row_in_tile;
-      mbar_wait(bar(H1_FULL + b), (it >> 1) & 1);
-      mbar_wait(bar(A2_EMPTY), (it & 1) ^ 1);     // layer 2 of the previous tile has consumed A2
+      mbar_wait(bar(H1_FULL + b), (it >> 1) & 1, (a.mode & 64) ? 200 : 0);
+      if (tid == 0) DSMIL_TRACE(2, 0, it);
+      mbar_wait(bar(A2_EMPTY), (it & 1) ^ 1, (a.mode & 64) ? 200 : 0);     // layer 2 of the previous tile has consumed A2
+      if (tid == 0) DSMIL_TRACE(2, 3, it);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < kQ; c0 += 32) {
-        uint32_t v[32];
-        DSMIL_TMEM_LD32(tm_h1[b] + lane_sel + c0, v);
+      for (int c0 = col0; c0 < col0 + 64; c0 += 16) {
+        uint32_t v[16];
+        DSMIL_TMEM_LD16((b ? tm_h1_1 : tm_h1_0) + lane_sel + c0, v);
         tmem_wait_ld();
-        uint32_t hi[16], lo[16];
+        uint32_t hi[8], lo[8];
+        if (a.mode & 16) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float h0 = fmaxf(__uint_as_float(v[2 * q]) + s_b1[c0 + 2 * q], 0.f);
-          const float h1 = fmaxf(__uint_as_float(v[2 * q + 1]) + s_b1[c0 + 2 * q + 1], 0.f);
+          for (int q = 0; q < 8; ++q) { hi[q] = v[2 * q]; lo[q] = v[2 * q + 1]; }
+        } else
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float2 bb = *reinterpret_cast<const float2*>(&s_b1[c0 + 2 * q]);
+          const float h0 = fmaxf(__uint_as_float(v[2 * q]) + bb.x, 0.f);
+          const float h1 = fmaxf(__uint_as_float(v[2 * q + 1]) + bb.y, 0.f);
           v[2 * q] = __float_as_uint(h0);
           v[2 * q + 1] = __float_as_uint(h1);
           const __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1);
@@ -411,12 +564,12 @@ k_qmlp_sm100(const QmlpArgs a) {
           hi[q] = *reinterpret_cast<const uint32_t*>(&hh);
           lo[q] = *reinterpret_cast<const uint32_t*>(&ll);
         }
-        DSMIL_TMEM_ST16(tm_a2hi + lane_sel + (c0 >> 1), hi);
-        DSMIL_TMEM_ST16(tm_a2lo + lane_sel + (c0 >> 1), lo);
-        if (a.H1 != nullptr && n < a.N) {
-          float4* dst = reinterpret_cast<float4*>(a.H1 + n * kQ + c0);
+        DSMIL_TMEM_ST8(tm_a2hi + lane_sel + (c0 >> 1), hi);
+        DSMIL_TMEM_ST8(tm_a2lo + lane_sel + (c0 >> 1), lo);
+        if (a.H1 != nullptr && live) {
+          float4* dst = reinterpret_cast<float4*>(a.H1 + grow * kQ + c0);
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
+          for (int q = 0; q < 4; ++q)
             dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
                                  __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
         }
@@ -425,43 +578,72 @@ k_qmlp_sm100(const QmlpArgs a) {
       tc_fence_before();
       mbar_arrive(bar(H1_EMPTY + b));
       mbar_arrive(bar(A2_FULL));
-      if (it > 0) q_epilogue(it - 1, prev_tile);
-      prev_tile = tile;
+      if (tid == 0) DSMIL_TRACE(2, 1, it);
+      if (it > 0) q_epilogue(it - 1, prev_grow, prev_live);
+      if (tid == 0) DSMIL_TRACE(2, 2, it);
+      prev_grow = grow;
+      prev_live = live;
     }
-    if (it > 0) q_epilogue(it - 1, prev_tile);
+    if (it > 0) q_epilogue(it - 1, prev_grow, prev_live);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kWarpMma) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+// one kernel for both images
+__global__ void __launch_bounds__(256)
+k_prep_wimg2(const float* __restrict__ W1, int D, const float* __restrict__ W2, uint8_t* __restrict__ img1,
+             uint8_t* __restrict__ img2) {
+  const int t1 = 128 * D, total = t1 + 128 * kQ;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const bool first = i < t1;
+    const int K = first ? D : kQ;
+    const int j = first ? i : i - t1;
+    const int n = j / K, k = j % K;
+    const float w = first ? W1[j] : W2[j];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+    uint8_t* chunk = (first ? img1 : img2) + static_cast<size_t>(k / kChunkK) * kChunkBytes;
+    const uint32_t off = swz_off(n, k % kChunkK);
+    *reinterpret_cast<__nv_bfloat16*>(chunk + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(chunk + kTileBytes + off) = lo;
   }
 }
 
 inline size_t qmlp_smem_bytes(int C, int D) { return kSmemFixed + sizeof(float) * C * D + 1024; }
 inline size_t wimg_bytes(int D) { return static_cast<size_t>(D / kChunkK) * kChunkBytes + 2 * kChunkBytes; }
 inline bool qmlp_supported(const dsmil_params_t* p) {
-  return p->nonlinear && p->D % kChunkK == 0 && p->D >= kChunkK && qmlp_smem_bytes(p->C, p->D) <= 232448 &&
-         (reinterpret_cast<uintptr_t>(p->W1) % 4 == 0);
+  return p->nonlinear && p->D % (2 * kChunkK) == 0 && qmlp_smem_bytes(p->C, p->D) <= 232448;
 }
 
-// scores + arg-max keys + Q (+H1) for N rows.  wimg: >= wimg_bytes(D) bytes of workspace.
-inline int launch_qmlp(const dsmil_params_t* p, const float* X, int64_t N, float* classes,
-                       unsigned long long* keys, float* Q, float* H1, uint8_t* wimg, int num_sms,
-                       cudaStream_t st) {
+inline int launch_prep_wimg(const dsmil_params_t* p, uint8_t* wimg, cudaStream_t st) {
+  uint8_t* w2img = wimg + static_cast<size_t>(p->D / kChunkK) * kChunkBytes;
+  k_prep_wimg2<<<80, 256, 0, st>>>(p->W1, p->D, p->W2, wimg, w2img);
+  DSMIL_LAUNCH_OK("k_prep_wimg2");
+  return 0;
+}
+
+// scores + arg-max keys + Q (+H1) for the tiles [tile0, tile0+ntiles) of bags [bag0, bag0+nb).
+// wimg must already hold the images (launch_prep_wimg).
+inline int launch_qmlp(const dsmil_params_t* p, const BagDev* bags_dev, int bag0, int nb, int tile0, int ntiles,
+                       float* classes, unsigned long long* keys, float* Q, float* H1, const uint8_t* wimg,
+                       int num_sms, cudaStream_t st) {
   const int D = p->D, C = p->C;
-  uint8_t* w1img = wimg;
-  uint8_t* w2img = wimg + static_cast<size_t>(D / kChunkK) * kChunkBytes;
-  k_prep_wimg<<<64, 256, 0, st>>>(p->W1, D, w1img);
-  DSMIL_LAUNCH_OK("k_prep_wimg(W1)");
-  k_prep_wimg<<<16, 256, 0, st>>>(p->W2, kQ, w2img);
-  DSMIL_LAUNCH_OK("k_prep_wimg(W2)");
-  QmlpArgs a{X, N, D, C, p->Wi, p->bi, p->b1, p->b2, w1img, w2img, classes, keys, Q, H1};
+  const uint8_t* w2img = wimg + static_cast<size_t>(D / kChunkK) * kChunkBytes;
+  QmlpArgs a{bags_dev, bag0, nb, tile0, ntiles, D, C, p->Wi, p->bi, p->b1, p->b2, wimg, w2img, classes, keys, Q, H1,
+             g_trace_buf, debug_mode()};
   const size_t smem = qmlp_smem_bytes(C, D);
-  const int64_t tiles = (N + kTileM - 1) / kTileM;
-  const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
+  const int grid = ntiles < num_sms ? ntiles : num_sms;
   auto go = [&](auto kern) -> int {
-    DSMIL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    static size_t configured = 0;   // per instantiation
+    if (configured < smem) {
+      DSMIL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      configured = smem;
+    }
     prof_begin(PROF_FUSED, st);
     kern<<<grid, kThreads, smem, st>>>(a);
     prof_end(PROF_FUSED, st);

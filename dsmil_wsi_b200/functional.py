@@ -213,3 +213,41 @@ def mil_forward(feats, params: Sequence[Optional[torch.Tensor]], v_input=None, v
                 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """Returns (classes, prediction_bag, A, B, crit_idx)."""
     return MILForwardFn.apply(feats, v_input, v_mask, classes_in, *params)
+
+
+@torch.no_grad()
+def mil_forward_bags(bags: Sequence[torch.Tensor], params: Sequence[Optional[torch.Tensor]]):
+    """Inference forward of a STREAM of bags in one library call (dsmil_forward_bags): returns a list of
+    (classes, prediction_bag, A, B) per bag -- views into packed device buffers -- plus crit_idx [nb, C]."""
+    lib = _lib.load()
+    P = ParamPack(*params)
+    if P.passing_v:
+        raise NotImplementedError("forward_bags: passing_v models go through MILNet.forward per bag")
+    xs = [_check_feats(b, P.D) for b in bags]
+    nb = len(xs)
+    if nb == 0:
+        return [], None
+    Ns = [int(x.shape[0]) for x in xs]
+    if min(Ns) == 0:
+        raise IndexError("dsmil_b200: empty bag (N == 0) in the batch")
+    dev = P.device
+    for x in xs:
+        if x.device != dev:
+            raise RuntimeError(f"dsmil_b200: bag on {x.device} but parameters on {dev}")
+    total, Cc, D = sum(Ns), P.C, P.D
+    c_N = (C.c_int64 * nb)(*Ns)
+    c_X = (C.c_void_p * nb)(*[x.data_ptr() for x in xs])
+    with torch.cuda.device(dev):
+        new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        classes, A = new(total, Cc), new(total, Cc)
+        pred, B = new(nb, Cc), new(nb, Cc, D)
+        crit = torch.empty(nb, Cc, dtype=torch.int64, device=dev)
+        ws = _workspace(lib.dsmil_forward_bags_workspace_bytes(P.ref, c_N, nb), dev)
+        rc = lib.dsmil_forward_bags(P.ref, c_X, c_N, nb, _ptr(classes), _ptr(pred), _ptr(A), _ptr(B), _ptr(crit),
+                                    _ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, "dsmil_forward_bags")
+    outs, row = [], 0
+    for b, n in enumerate(Ns):
+        outs.append((classes[row:row + n], pred[b:b + 1], A[row:row + n], B[b:b + 1]))
+        row += n
+    return outs, crit

@@ -131,6 +131,23 @@ class MILNet(nn.Module):
         return classes, prediction_bag, A, B
 
     @torch.no_grad()
+    def forward_bags(self, bags):
+        """Throughput form: a list of bags [N_i, D] -> list of (classes, prediction_bag, A, B), computed by ONE
+        library call (bag table, L2-sized sub-batches).  Inference only (no autograd)."""
+        ic, bc = self.i_classifier, self.b_classifier
+        if not (isinstance(bc, BClassifier) and isinstance(ic, (FCLayer, IClassifier))):
+            return [self.forward(b) for b in bags]
+        feats = [ic.embed(b) if isinstance(ic, IClassifier) else b for b in bags]
+        lin = ic._linear()
+        W1, b1, W2, b2 = bc._q_params()
+        Wv, bv, _ = bc._v_params()
+        if Wv is not None:
+            return [self.forward(b) for b in bags]
+        params = (lin.weight, lin.bias, W1, b1, W2, b2, None, None, bc.fcc.weight, bc.fcc.bias)
+        outs, _ = Fn.mil_forward_bags(feats, params)
+        return outs
+
+    @torch.no_grad()
     def critical_instances(self, x):
         """Indices dsmil.py:52-53 selects (row 0 of the descending sort), lowest index on ties."""
         ic, bc = self.i_classifier, self.b_classifier

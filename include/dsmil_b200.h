@@ -80,6 +80,9 @@ uint64_t dsmil_launch_count(void);
  * 3 finalize, 4 fused tcgen05 kernel) and resets the log.  Not thread-safe; bench use only. */
 int dsmil_profile_enable(int on);
 int dsmil_profile_read(double* ms_per_tag, uint64_t* launches_per_tag);
+/* Debug aid: when buf (device int64[3*8*64]) is non-NULL, CTA 0 of the tensor-core kernel stores clock64
+ * stamps of its pipeline events there (tools/ktrace.py decodes them).  NULL disables. */
+int dsmil_debug_set_trace(void* buf);
 /* Which kernel family the forward would use for (D,C): 1 = generic fp32 FFMA, 2 = sm_100a tcgen05. */
 int dsmil_forward_path(const dsmil_params_t* p, int64_t N);
 
@@ -96,6 +99,15 @@ int dsmil_forward(const dsmil_params_t* p, const float* X, const float* x_for_v,
                   float* classes, float* pred, float* A, float* B, int64_t* crit_idx,
                   float* save_Q, float* save_H1, float* save_V,
                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* A stream of bags in ONE call (throughput form of the same forward; slides/sec in BASELINE.json):
+ * Xs[b] -> device features [Ns[b], D] (host arrays of nb entries).  Outputs are packed in bag order:
+ * classes / A [sum N, C], pred [nb, C], B [nb, C, D], crit_idx [nb, C].  On the tensor-core path the
+ * whole batch costs a handful of launches (bag table + L2-sized sub-batches); other shapes loop. */
+size_t dsmil_forward_bags_workspace_bytes(const dsmil_params_t* p, const int64_t* Ns, int32_t nb);
+int dsmil_forward_bags(const dsmil_params_t* p, const float* const* Xs, const int64_t* Ns, int32_t nb,
+                       float* classes, float* pred, float* A, float* B, int64_t* crit_idx,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* Call form (2)+(3) of the boundary: the callers in attention_map.py:74,85 /
  * testing_tcga.py:72,83 run the instance classifier and the bag classifier separately.

@@ -281,3 +281,32 @@ def test_tensor_core_q_mlp_matches_fp64(name):
     assert rel_to_max(_np(classes), t.classes) < TOL_CLS
     idx = _np(cand)[: 2 * p.C].view(np.int64)
     assert np.array_equal(idx, t.idx)
+
+
+def test_forward_bags_matches_per_bag_forward_and_oracle():
+    """Throughput API: ragged batch of bags in one call == per-bag forward == fp64 oracle."""
+    p = orc.random_params(512, 2, 41, scale=2.0)
+    net = build_net(p).eval()
+    sizes = [1, 127, 128, 129, 1000, 4097, 10000, 300]
+    Xs = [orc.synthetic_bag(n, 512, 600 + i, "uniform" if i % 2 else "normal") for i, n in enumerate(sizes)]
+    xs = [torch.from_numpy(x).cuda() for x in Xs]
+    with torch.no_grad():
+        outs = net.forward_bags(xs)
+        singles = [net(x) for x in xs]
+    assert len(outs) == len(sizes)
+    for i, (o, s, X) in enumerate(zip(outs, singles, Xs)):
+        for u, v in zip(o, s):
+            assert u.shape == v.shape and torch.equal(u, v), (i, sizes[i])
+        t = orc.forward(X, p)
+        _check_forward(o, t.classes, t.prediction_bag, t.A, t.B, t.idx, p, None, f"bags[{i}] N={sizes[i]}")
+
+
+def test_forward_bags_generic_shapes_loop():
+    p = orc.random_params(166, 1, 43)
+    net = build_net(p).eval()
+    Xs = [orc.synthetic_bag(n, 166, 700 + n, "normal") for n in (3, 17, 40)]
+    with torch.no_grad():
+        outs = net.forward_bags([torch.from_numpy(x).cuda() for x in Xs])
+    for o, X in zip(outs, Xs):
+        t = orc.forward(X, p)
+        _check_forward(o, t.classes, t.prediction_bag, t.A, t.B, t.idx, p, None, "generic bags")
