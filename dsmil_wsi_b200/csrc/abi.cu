@@ -327,8 +327,11 @@ static size_t l2_budget_bytes() {
   static size_t v = 0;
   if (!v) {
     const char* e = getenv("DSMIL_B200_L2_MB");
-    const long mb = e ? atol(e) : 72;
-    v = static_cast<size_t>(mb > 0 ? mb : 72) << 20;
+    // Default: no sub-batching.  At the kernels' current speed a second HBM read of X (3 us per 10k-row bag)
+    // costs less than the wave quantisation of small launches; set e.g. DSMIL_B200_L2_MB=72 to keep each
+    // sub-batch L2-resident between phase 1 and phase 2 instead.
+    const long mb = e ? atol(e) : (1l << 20);
+    v = static_cast<size_t>(mb > 0 ? mb : (1l << 20)) << 20;
   }
   return v;
 }

@@ -29,14 +29,14 @@ constexpr int kTileBytes = kTileM * kChunkK * 2;       // 16 KiB: one [128 x 64]
 constexpr int kChunkBytes = 2 * kTileBytes;            // hi tile + lo tile
 constexpr int kAStages = 2;
 constexpr int kWStages = 2;
-constexpr int kConvWarps = 8;
+constexpr int kConvWarps = 16;           // 512 converter threads: 4 float4 per thread per 32 KB chunk
 constexpr int kEpiWarps = 8;             // two warps per TMEM lane quadrant, each takes 64 of the 128 columns
 // Roles are aligned to warpgroups (4 warps) so that setmaxnreg can move registers between them:
 // WG0-1 epilogue | WG2-3 converters | WG4 = MMA issuer, W producer, 2 idle warps
 constexpr int kWarpConv0 = kEpiWarps, kWarpMma = kEpiWarps + kConvWarps, kWarpTma = kWarpMma + 1;
 constexpr int kThreads = 32 * (kEpiWarps + kConvWarps + 4);
-// The pool is what the CTA got at launch: 96 regs x 640 threads = 61440 (an .inc blocks until .dec frees enough)
-constexpr int kRegsConv = 136, kRegsEpi = 88, kRegsCtl = 32;   // 256*136 + 256*88 + 128*32 = 61440
+// The pool is what the CTA got at launch: 72 regs x 896 threads = 64512 (an .inc blocks until .dec frees enough)
+constexpr int kRegsConv = 72, kRegsEpi = 88, kRegsCtl = 40;    // 512*72 + 256*88 + 128*40 = 64512
 template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {   // read-once data: keep it out of L1
@@ -293,98 +293,80 @@ k_qmlp_sm100(const QmlpArgs a) {
 
   if (warp >= kWarpConv0 && warp < kWarpMma) {
     // =============================== converter warps =========================================
-    reg_inc<kRegsConv>();
-    const int ct = tid - kWarpConv0 * 32;        // 0..255
-    const int seg = ct & 15, r0 = ct >> 4;       // float4 index in the 64-float chunk row; base row
+    // (stay at the launch register count; the epilogue's .inc is fed by the control warps' .dec)
+    const int ct = tid - kWarpConv0 * 32;        // 0..511
+    const int seg = ct & 15, r0 = ct >> 4;       // float4 index in the 64-float chunk row; base row (0..31)
+    const uint32_t off0 = swz_off(r0, seg * 4);  // rows r0 + 32 i share (row & 7): offset_i = off0 + 4096 i
     uint32_t stage = 0, phase = 0;
     TileCursor cur_bag(a.bags, a.bag0, a.nb);
-    for (int tile = a.tile0 + blockIdx.x; tile < tile_end; tile += gridDim.x) {
-      cur_bag.seek(tile);
-      const BagDev bg = a.bags[cur_bag.bag];
-      const long long row_base = static_cast<long long>(tile - bg.tile_off) * kTileM;   // row inside the bag
-      float sc[8][CT];
+    // The loop is flat over (tile, k-chunk): `nxt` always holds the NEXT chunk -- of this tile or the first
+    // chunk of the CTA's next tile -- so the HBM stream never drains at a tile boundary.
+    int tile = a.tile0 + blockIdx.x;
+    // state of the tile whose chunks are being LOADED (may already be the next tile): 32-bit row numbers
+    uint32_t ld_N = 0, ld_row = 0;               // rows in the bag, first row of the tile (+ r0)
+    long long ld_rowoff = 0;
+    const float4* xrow = nullptr;
+    auto open_tile = [&](int t) {
+      cur_bag.seek(t);
+      const BagDev* bp = a.bags + cur_bag.bag;
+      ld_N = static_cast<uint32_t>(bp->N);
+      ld_rowoff = bp->row_off;
+      ld_row = static_cast<uint32_t>(t - bp->tile_off) * kTileM + r0;
+      xrow = reinterpret_cast<const float4*>(bp->X + static_cast<long long>(ld_row) * D) + seg;
+    };
+    auto load_chunk = [&](int kc, float4* dst) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4; ++i) {
+        const float4* src = xrow + static_cast<long long>(i) * (8ll * D) + kc * (kChunkK / 4);   // 32 rows apart
+        dst[i] = (ld_row + 32 * i < ld_N) ? ldg_stream(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    float4 cur[4], nxt[4];
+    if (tile < tile_end) { open_tile(tile); load_chunk(0, cur); }
+    while (tile < tile_end) {
+      const int my_bag = cur_bag.bag;            // this tile's bag (the load state may move on below)
+      const uint32_t t_N = ld_N, t_row = ld_row;
+      const long long t_rowoff = ld_rowoff;
+      float sc[4][CT];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int k = 0; k < CT; ++k) sc[i][k] = 0.f;
-      const bool full = row_base + kTileM <= bg.N;
-      const float4* xrow = reinterpret_cast<const float4*>(bg.X + (row_base + r0) * D) + seg;
-      const long long rstride4 = 4ll * D;          // 16 rows, in float4 units
-      // Half-chunk h = (k-chunk h>>1, row half h&1): 4 float4 per thread.  Four register buffers, loads are
-      // issued three half-chunks (48 KB per SM) ahead of their use to cover the HBM latency.
-      auto load_half = [&](int h, float4* dst) {
-        const int kc = h >> 1, part = h & 1;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int ri = i + 4 * part;
-          const float4* src = xrow + ri * rstride4 + kc * (kChunkK / 4);
-          dst[i] = (full || row_base + r0 + 16 * ri < bg.N) ? ldg_stream(src) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      const uint32_t off0 = swz_off(r0, seg * 4);  // rows r0 + 16 i share (row & 7): offset_i = off0 + 2048 i
-      float4 wk[CT];
-      uint8_t* hi_tile = nullptr;
-      auto proc_half = [&](int h, const float4* src, auto part_c) {
-        constexpr int part = decltype(part_c)::value;
-        const int kc = h >> 1;
-        if (part == 0) {
-#pragma unroll
-          for (int k = 0; k < CT; ++k)
-            wk[k] = (do_scores && k < C) ? *reinterpret_cast<const float4*>(sWi + k * D + kc * kChunkK + seg * 4)
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ct == 0 && tile == a.tile0 + 2 * static_cast<int>(gridDim.x)) DSMIL_TRACE(0, 0, kc);   // chunk start
-          mbar_wait(bar(A_EMPTY + stage), phase ^ 1);
-          if (ct == 0 && tile == a.tile0 + 2 * static_cast<int>(gridDim.x)) DSMIL_TRACE(0, 1, kc);   // stage free
-          hi_tile = smem + kOffARing + stage * kChunkBytes + off0;
-        }
+      const int next_tile = tile + gridDim.x;
+      for (int kc = 0; kc < nchunks; ++kc) {
+        if (kc + 1 < nchunks) load_chunk(kc + 1, nxt);
+        else if (next_tile < tile_end) { open_tile(next_tile); load_chunk(0, nxt); }
+        mbar_wait(bar(A_EMPTY + stage), phase ^ 1);
+        uint8_t* hi_tile = smem + kOffARing + stage * kChunkBytes + off0;
         uint8_t* lo_tile = hi_tile + kTileBytes;
-        if (a.mode & 4) {   // experiment: consume the loads, no conversion
-          float t = 0.f;
+        {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) t += src[i].x + src[i].w;
-          if (t == 123456.f) *reinterpret_cast<float*>(hi_tile) = t;
-        } else
+          for (int i = 0; i < 4; ++i) {
+            const float4 x = cur[i];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 x = src[i];
-          if (part == 0 && i == 0 && ct == 0 && tile == a.tile0 + 2 * static_cast<int>(gridDim.x)) { if (x.x == 123456.f) DSMIL_TRACE(0, 5, kc); DSMIL_TRACE(0, 2, kc); }
-#pragma unroll
-          for (int k = 0; k < CT; ++k) {
-            float s = sc[i + 4 * part][k];
-            s = fmaf(x.x, wk[k].x, s); s = fmaf(x.y, wk[k].y, s); s = fmaf(x.z, wk[k].z, s); s = fmaf(x.w, wk[k].w, s);
-            sc[i + 4 * part][k] = s;
+            for (int k = 0; k < CT; ++k)
+              if (do_scores && k < C) {
+                const float4 w = *reinterpret_cast<const float4*>(sWi + k * D + kc * kChunkK + seg * 4);
+                float s = sc[i][k];
+                s = fmaf(x.x, w.x, s); s = fmaf(x.y, w.y, s); s = fmaf(x.z, w.z, s); s = fmaf(x.w, w.w, s);
+                sc[i][k] = s;
+              }
+            const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
+            const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - __low2float(h01), x.y - __high2float(h01));
+            const __nv_bfloat162 l23 = __floats2bfloat162_rn(x.z - __low2float(h23), x.w - __high2float(h23));
+            uint2 hv, lv;
+            hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+            lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+            *reinterpret_cast<uint2*>(hi_tile + i * 4096) = hv;
+            *reinterpret_cast<uint2*>(lo_tile + i * 4096) = lv;
           }
-          const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
-          const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - __low2float(h01), x.y - __high2float(h01));
-          const __nv_bfloat162 l23 = __floats2bfloat162_rn(x.z - __low2float(h23), x.w - __high2float(h23));
-          uint2 hv, lv;
-          hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-          lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-          *reinterpret_cast<uint2*>(hi_tile + (i + 4 * part) * 2048) = hv;
-          *reinterpret_cast<uint2*>(lo_tile + (i + 4 * part) * 2048) = lv;
         }
-        if (part == 1) {
-          if (!(a.mode & 128)) fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(A_FULL + stage));
-          if (ct == 0 && tile == a.tile0 + 2 * static_cast<int>(gridDim.x)) DSMIL_TRACE(0, 3, kc);   // stage published
-          if (++stage == kAStages) { stage = 0; phase ^= 1; }
-        }
-      };
-      using P0 = std::integral_constant<int, 0>;
-      using P1 = std::integral_constant<int, 1>;
-      const int nh = 2 * nchunks;                  // multiple of 4 (D % 128 == 0)
-      float4 b0[4], b1[4], b2[4], b3[4];
-      load_half(0, b0); load_half(1, b1); load_half(2, b2);
-      for (int h = 0; h < nh; h += 4) {
-        load_half(h + 3, b3);
-        proc_half(h, b0, P0{});
-        if (h + 4 < nh) load_half(h + 4, b0);
-        proc_half(h + 1, b1, P1{});
-        if (h + 5 < nh) load_half(h + 5, b1);
-        proc_half(h + 2, b2, P0{});
-        if (h + 6 < nh) load_half(h + 6, b2);
-        proc_half(h + 3, b3, P1{});
+        fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (required: tested)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(A_FULL + stage));
+        if (++stage == kAStages) { stage = 0; phase ^= 1; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
       }
       // instance scores of this tile: reduce over the 16 threads (seg) that share a row; the per-class
       // arg-max key of the tile goes straight to the bag's key slot (one atomicMax per warp and class)
@@ -393,8 +375,8 @@ k_qmlp_sm100(const QmlpArgs a) {
 #pragma unroll
         for (int k = 0; k < CT; ++k) best[k] = 0ull;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const long long n = row_base + r0 + 16 * i;
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t n = t_row + 32 * i;
 #pragma unroll
           for (int k = 0; k < CT; ++k) {
             float v = sc[i][k];
@@ -402,10 +384,10 @@ k_qmlp_sm100(const QmlpArgs a) {
             v += __shfl_xor_sync(0xffffffffu, v, 4);
             v += __shfl_xor_sync(0xffffffffu, v, 2);
             v += __shfl_xor_sync(0xffffffffu, v, 1);
-            if (seg == 0 && k < C && n < bg.N) {
+            if (seg == 0 && k < C && n < t_N) {
               v += a.bi[k];
-              a.classes[(bg.row_off + n) * C + k] = v;
-              const unsigned long long key = pack_key(v, static_cast<uint32_t>(n));
+              a.classes[(t_rowoff + n) * C + k] = v;
+              const unsigned long long key = pack_key(v, n);
               best[k] = key > best[k] ? key : best[k];
             }
           }
@@ -413,9 +395,10 @@ k_qmlp_sm100(const QmlpArgs a) {
 #pragma unroll
         for (int k = 0; k < CT; ++k) {
           const unsigned long long b = warp_max_u64(best[k]);
-          if (lane == 0 && k < C && b) atomicMax(a.keys + static_cast<size_t>(cur_bag.bag) * kMaxC + k, b);
+          if (lane == 0 && k < C && b) atomicMax(a.keys + static_cast<size_t>(my_bag) * kMaxC + k, b);
         }
       }
+      tile = next_tile;
     }
   } else if (warp >= kWarpMma && warp != kWarpMma && warp != kWarpTma) {
     reg_dec<kRegsCtl>();     // idle warps of the control warpgroup
@@ -453,7 +436,7 @@ k_qmlp_sm100(const QmlpArgs a) {
         mbar_wait(bar(Q_EMPTY), (j & 1) ^ 1);
         DSMIL_TRACE(1, 5, j);
         tc_fence_after();
-#pragma unroll
+#pragma unroll 2
         for (int ks = 0; ks < ((a.mode & 8) ? 0 : 8); ++ks) {
           const uint32_t bhi = desc_lo(w2base + (ks >> 2) * kChunkBytes + (ks & 3) * 32);
           const uint32_t blo = bhi + (kTileBytes >> 4);
@@ -498,7 +481,7 @@ k_qmlp_sm100(const QmlpArgs a) {
     }
   } else {
     // ====== epilogue warps: TMEM lane quadrant = warp & 3, column half = warp >> 2 =============
-    reg_dec<kRegsEpi>();
+    reg_inc<kRegsEpi>();
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const int row_in_tile = (warp & 3) * 32 + lane;
     const int col0 = (warp >> 2) * 64;
