@@ -316,7 +316,12 @@ static BagsWs carve_bags(const dsmil_params_t* p, const int64_t* Ns, int nb, boo
   w.keys = c.take<unsigned long long>(static_cast<size_t>(nb) * (kMaxC + 1));
   w.counters = reinterpret_cast<unsigned int*>(w.keys ? w.keys + static_cast<size_t>(nb) * kMaxC : nullptr);
   w.pred_part = c.take<float>(static_cast<size_t>(nb) * sm100::kFinSlices * kMaxC);
-  w.Q = need_Q ? c.take<float>(static_cast<size_t>(total) * kQ) : nullptr;
+  {   // tile-blocked Q: one 128x128 block per 128-row tile
+    int64_t tiles = 0;
+    for (int b = 0; b < nb; ++b) tiles += (Ns[b] + sm100::kTileM - 1) / sm100::kTileM;
+    w.Q = need_Q ? c.take<float>(static_cast<size_t>(tiles) * sm100::kTileM * kQ) : nullptr;
+  }
+  (void)total;
   w.wimg = c.take<uint8_t>(sm100::wimg_bytes(p->D) + 1024);
   w.recs = c.take<float>(static_cast<size_t>(nrec) * rec_floats(p->C, p->D));
   w.bytes = c.off;
@@ -386,10 +391,11 @@ static int forward_bags_impl(const dsmil_params_t* p, const float* const* Xs, co
     const int t1 = (b1 < nb) ? tbl[b1].tile_off : tile;
     const int r0 = tbl[b0].rec_off;
     const int r1 = (b1 < nb) ? tbl[b1].rec_off : rec;
+    const int q_blocked = save_Q ? 0 : 1;   // training keeps Q row-major for the backward kernels
     if ((rc = sm100::launch_qmlp(p, w.table, b0, b1 - b0, t0, t1 - t0, classes_in ? nullptr : classes, w.keys, Q,
-                                 save_H1, img, num_sms(), st)))
+                                 save_H1, img, num_sms(), st, q_blocked)))
       return rc;
-    sm100::AttendArgs aa{w.table, b0, b1 - b0, r0, D, C, Q, w.keys, A, w.recs};
+    sm100::AttendArgs aa{w.table, b0, b1 - b0, r0, D, C, Q, q_blocked, w.keys, A, w.recs};
     if ((rc = sm100::launch_attend_b(aa, r1 - r0, st))) return rc;
     sm100::FinalizeArgs fa{w.table, b0, D, C, w.recs, w.keys, p->Wf, p->bf, A, B, pred,
                            reinterpret_cast<long long*>(crit), w.pred_part, w.counters};

@@ -20,7 +20,8 @@ struct AttendArgs {
   int bag0, nb;
   int rec0;                 // first record index covered by this launch (== blockIdx.x 0)
   int D, C;
-  const float* Q;           // packed [sumN,128]
+  const float* Q;           // packed [sumN,128] row-major, or tile-blocked column-major (q_blocked)
+  int q_blocked;
   const unsigned long long* keys;  // [nbags][kMaxC]
   float* A;                 // packed [sumN,C]: receives the raw logits here
   float* recs;              // [total records][rec_floats(C,D)]
@@ -52,7 +53,8 @@ k_attend_b(const AttendArgs a) {
     float v = 0.f;
     if (k < C) {
       const long long row = key_row(a.keys[static_cast<size_t>(bag) * kMaxC + k]);
-      v = a.Q[(bg.row_off + row) * kQ + j];
+      v = a.q_blocked ? a.Q[static_cast<size_t>(bg.tile_off + row / kAttRows) * (kAttRows * kQ) + j * kAttRows + (row % kAttRows)]
+                      : a.Q[(bg.row_off + row) * kQ + j];
     }
     sq[k][j] = v;
   }
@@ -71,7 +73,41 @@ k_attend_b(const AttendArgs a) {
   for (int t = cta_in_bag; t < ntiles; t += bg.nrec) {
     const long long r0 = static_cast<long long>(t) * kAttRows;
     const int rows = static_cast<int>((bg.N - r0) < kAttRows ? (bg.N - r0) : kAttRows);
-    // (a) logits: warp w owns rows w*16 .. w*16+15
+    // (a) logits
+    if (a.q_blocked) {
+      // thread (row = tid & 127, column half = tid >> 7): 64 coalesced column loads, no shuffles
+      const int r = tid & 127, hf = tid >> 7;
+      const float* qb = a.Q + static_cast<size_t>(bg.tile_off + t) * (kAttRows * kQ) + static_cast<size_t>(hf * 64) * kAttRows + r;
+      float d[CT];
+#pragma unroll
+      for (int k = 0; k < CT; ++k) d[k] = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < 64; c += 4) {
+        const float q0 = __ldg(qb + (c + 0) * kAttRows), q1 = __ldg(qb + (c + 1) * kAttRows);
+        const float q2 = __ldg(qb + (c + 2) * kAttRows), q3 = __ldg(qb + (c + 3) * kAttRows);
+#pragma unroll
+        for (int k = 0; k < CT; ++k) {
+          const float4 w = *reinterpret_cast<const float4*>(&sq[k][hf * 64 + c]);
+          d[k] = fmaf(q0, w.x, d[k]); d[k] = fmaf(q1, w.y, d[k]); d[k] = fmaf(q2, w.z, d[k]); d[k] = fmaf(q3, w.w, d[k]);
+        }
+      }
+      if (hf == 1) {
+#pragma unroll
+        for (int k = 0; k < CT; ++k) sE[r][k] = d[k];          // park the upper-half partial
+      }
+      __syncthreads();
+      if (hf == 0) {
+#pragma unroll
+        for (int k = 0; k < CT; ++k) {
+          float L = -INFINITY;
+          if (r < rows) {
+            L = __fdiv_rn(d[k] + sE[r][k], kScale);             // dsmil.py:56: a division by sqrt(128f)
+            if (k < C) a.A[(bg.row_off + r0 + r) * C + k] = L;
+          }
+          sL[r][k] = L;
+        }
+      }
+    } else
 #pragma unroll 4
     for (int rr = 0; rr < 16; ++rr) {
       const int r = warp * 16 + rr;

@@ -39,6 +39,14 @@ constexpr int kThreads = 32 * (kEpiWarps + kConvWarps + 4);
 constexpr int kRegsConv = 72, kRegsEpi = 88, kRegsCtl = 40;    // 512*72 + 256*88 + 128*40 = 64512
 template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {   // read-once data: keep it out of L1
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -206,9 +214,10 @@ struct QmlpArgs {
   const uint8_t* w2img;   // 2 chunks
   float* classes;         // packed [sumN, C] or NULL (scores given by the caller)
   unsigned long long* keys;  // [nbags][kMaxC]
-  float* Q;               // packed [sumN,128]
+  float* Q;               // packed row-major [sumN,128], or (q_blocked) per-tile column-major blocks [tile][128 col][128 row]
   float* H1;              // packed [sumN,128] or NULL
   long long* dbg;         // optional timeline of CTA 0 (clock64 stamps), see DSMIL_B200_TRACE in abi.cu
+  int q_blocked;          // 1: Q is written in tile blocks (coalesced epilogue stores; inference path)
   int mode;               // timing experiments only (DSMIL_B200_DEBUG_MODE): bit0 no Q stores, bit1 no scores,
                           // bit2 converter skips convert+store, bit3 no MMAs, bit4 epilogue skips math
 };
@@ -297,6 +306,7 @@ k_qmlp_sm100(const QmlpArgs a) {
     const int ct = tid - kWarpConv0 * 32;        // 0..511
     const int seg = ct & 15, r0 = ct >> 4;       // float4 index in the 64-float chunk row; base row (0..31)
     const uint32_t off0 = swz_off(r0, seg * 4);  // rows r0 + 32 i share (row & 7): offset_i = off0 + 4096 i
+    const uint32_t a_ring_u32 = smem_u32(smem + kOffARing), swi_u32 = smem_u32(smem + kOffWi);
     uint32_t stage = 0, phase = 0;
     TileCursor cur_bag(a.bags, a.bag0, a.nb);
     // The loop is flat over (tile, k-chunk): `nxt` always holds the NEXT chunk -- of this tile or the first
@@ -337,8 +347,9 @@ k_qmlp_sm100(const QmlpArgs a) {
         if (kc + 1 < nchunks) load_chunk(kc + 1, nxt);
         else if (next_tile < tile_end) { open_tile(next_tile); load_chunk(0, nxt); }
         mbar_wait(bar(A_EMPTY + stage), phase ^ 1);
-        uint8_t* hi_tile = smem + kOffARing + stage * kChunkBytes + off0;
-        uint8_t* lo_tile = hi_tile + kTileBytes;
+        const uint32_t hi_tile = a_ring_u32 + stage * kChunkBytes + off0;   // shared-space addresses: STS/LDS,
+        const uint32_t lo_tile = hi_tile + kTileBytes;                       // immediates instead of 64-bit math
+        const uint32_t w_addr = swi_u32 + static_cast<uint32_t>(kc * kChunkK + seg * 4) * 4u;
         {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -346,7 +357,7 @@ k_qmlp_sm100(const QmlpArgs a) {
 #pragma unroll
             for (int k = 0; k < CT; ++k)
               if (do_scores && k < C) {
-                const float4 w = *reinterpret_cast<const float4*>(sWi + k * D + kc * kChunkK + seg * 4);
+                const float4 w = lds128(w_addr + static_cast<uint32_t>(k * D) * 4u);
                 float s = sc[i][k];
                 s = fmaf(x.x, w.x, s); s = fmaf(x.y, w.y, s); s = fmaf(x.z, w.z, s); s = fmaf(x.w, w.w, s);
                 sc[i][k] = s;
@@ -354,11 +365,8 @@ k_qmlp_sm100(const QmlpArgs a) {
             const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
             const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - __low2float(h01), x.y - __high2float(h01));
             const __nv_bfloat162 l23 = __floats2bfloat162_rn(x.z - __low2float(h23), x.w - __high2float(h23));
-            uint2 hv, lv;
-            hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-            lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-            *reinterpret_cast<uint2*>(hi_tile + i * 4096) = hv;
-            *reinterpret_cast<uint2*>(lo_tile + i * 4096) = lv;
+            sts64(hi_tile + i * 4096, *reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+            sts64(lo_tile + i * 4096, *reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
           }
         }
         fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (required: tested)
@@ -485,7 +493,7 @@ k_qmlp_sm100(const QmlpArgs a) {
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const int row_in_tile = (warp & 3) * 32 + lane;
     const int col0 = (warp >> 2) * 64;
-    auto q_epilogue = [&](int j, long long grow, bool live) {   // grow: packed row index of this thread's row
+    auto q_epilogue = [&](int j, long long grow, bool live, int qtile) {   // grow: packed row of this thread
       mbar_wait(bar(Q_FULL), j & 1, (a.mode & 64) ? 200 : 0);
       tc_fence_after();
 #pragma unroll 1
@@ -494,7 +502,18 @@ k_qmlp_sm100(const QmlpArgs a) {
         DSMIL_TMEM_LD16(tm_q + lane_sel + c0, v);
         tmem_wait_ld();
         if (c0 == col0 + 48) { tc_fence_before(); mbar_arrive(bar(Q_EMPTY)); }
-        if (live && !(a.mode & 16)) {
+        if (a.q_blocked) {
+          // tile-blocked, column-major: lanes (= rows) are contiguous -> every store is one 128-byte line
+          float* dst = a.Q + static_cast<size_t>(qtile) * (kTileM * kQ) + static_cast<size_t>(c0) * kTileM + row_in_tile;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 bb = *reinterpret_cast<const float4*>(&s_b2[c0 + 4 * q]);
+            dst[(4 * q + 0) * kTileM] = fast_tanh(__uint_as_float(v[4 * q + 0]) + bb.x);
+            dst[(4 * q + 1) * kTileM] = fast_tanh(__uint_as_float(v[4 * q + 1]) + bb.y);
+            dst[(4 * q + 2) * kTileM] = fast_tanh(__uint_as_float(v[4 * q + 2]) + bb.z);
+            dst[(4 * q + 3) * kTileM] = fast_tanh(__uint_as_float(v[4 * q + 3]) + bb.w);
+          }
+        } else if (live && !(a.mode & 16)) {
           float4* dst = reinterpret_cast<float4*>((a.mode & 1) ? a.Q + (threadIdx.x & 255) * 4 : a.Q + grow * kQ + c0);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -509,7 +528,7 @@ k_qmlp_sm100(const QmlpArgs a) {
         }
       }
     };
-    int it = 0;
+    int it = 0, prev_tile = 0;
     long long prev_grow = 0;
     bool prev_live = false;
     TileCursor cur_bag(a.bags, a.bag0, a.nb);
@@ -562,12 +581,13 @@ k_qmlp_sm100(const QmlpArgs a) {
       mbar_arrive(bar(H1_EMPTY + b));
       mbar_arrive(bar(A2_FULL));
       if (tid == 0) DSMIL_TRACE(2, 1, it);
-      if (it > 0) q_epilogue(it - 1, prev_grow, prev_live);
+      if (it > 0) q_epilogue(it - 1, prev_grow, prev_live, prev_tile);
       if (tid == 0) DSMIL_TRACE(2, 2, it);
       prev_grow = grow;
       prev_live = live;
+      prev_tile = tile;
     }
-    if (it > 0) q_epilogue(it - 1, prev_grow, prev_live);
+    if (it > 0) q_epilogue(it - 1, prev_grow, prev_live, prev_tile);
   }
   tc_fence_before();
   __syncthreads();
@@ -614,11 +634,11 @@ inline int launch_prep_wimg(const dsmil_params_t* p, uint8_t* wimg, cudaStream_t
 // wimg must already hold the images (launch_prep_wimg).
 inline int launch_qmlp(const dsmil_params_t* p, const BagDev* bags_dev, int bag0, int nb, int tile0, int ntiles,
                        float* classes, unsigned long long* keys, float* Q, float* H1, const uint8_t* wimg,
-                       int num_sms, cudaStream_t st) {
+                       int num_sms, cudaStream_t st, int q_blocked = 0) {
   const int D = p->D, C = p->C;
   const uint8_t* w2img = wimg + static_cast<size_t>(D / kChunkK) * kChunkBytes;
   QmlpArgs a{bags_dev, bag0, nb, tile0, ntiles, D, C, p->Wi, p->bi, p->b1, p->b2, wimg, w2img, classes, keys, Q, H1,
-             g_trace_buf, debug_mode()};
+             g_trace_buf, q_blocked, debug_mode()};
   const size_t smem = qmlp_smem_bytes(C, D);
   const int grid = ntiles < num_sms ? ntiles : num_sms;
   auto go = [&](auto kern) -> int {
