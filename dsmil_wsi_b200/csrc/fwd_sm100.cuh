@@ -36,7 +36,7 @@ constexpr int kEpiWarps = 8;             // two warps per TMEM lane quadrant, ea
 constexpr int kWarpConv0 = kEpiWarps, kWarpMma = kEpiWarps + kConvWarps, kWarpTma = kWarpMma + 1;
 constexpr int kThreads = 32 * (kEpiWarps + kConvWarps + 4);
 // The pool is what the CTA got at launch: 72 regs x 896 threads = 64512 (an .inc blocks until .dec frees enough)
-constexpr int kRegsConv = 72, kRegsEpi = 88, kRegsCtl = 40;    // 512*72 + 256*88 + 128*40 = 64512
+constexpr int kRegsConv = 80, kRegsEpi = 72, kRegsCtl = 40;    // 512*80 + 256*72 + 128*40 = 64512
 template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
@@ -276,7 +276,7 @@ k_qmlp_sm100(const QmlpArgs a) {
   float* sWi = reinterpret_cast<float*>(smem + kOffWi);
   const bool do_scores = a.classes != nullptr && !(a.mode & 2);   // bag form (scores given): Wi/bi may be NULL
   if (do_scores)
-    for (int i = tid; i < C * D; i += kThreads) sWi[i] = a.Wi[i];
+    for (int i = tid; i < CT * D; i += kThreads) sWi[i] = (i < C * D) ? a.Wi[i] : 0.f;
   if (tid < kQ) { s_b1[tid] = a.b1[tid]; s_b2[tid] = a.b2[tid]; }
   if (tid == 0) {
     for (int s = 0; s < kAStages; ++s) { mbar_init(bar(A_FULL + s), kConvWarps); mbar_init(bar(A_EMPTY + s), 1); }
@@ -302,7 +302,7 @@ k_qmlp_sm100(const QmlpArgs a) {
 
   if (warp >= kWarpConv0 && warp < kWarpMma) {
     // =============================== converter warps =========================================
-    // (stay at the launch register count; the epilogue's .inc is fed by the control warps' .dec)
+    reg_inc<kRegsConv>();                        // fed by the control warps' .dec
     const int ct = tid - kWarpConv0 * 32;        // 0..511
     const int seg = ct & 15, r0 = ct >> 4;       // float4 index in the 64-float chunk row; base row (0..31)
     const uint32_t off0 = swz_off(r0, seg * 4);  // rows r0 + 32 i share (row & 7): offset_i = off0 + 4096 i
@@ -333,48 +333,57 @@ k_qmlp_sm100(const QmlpArgs a) {
     };
     float4 cur[4], nxt[4];
     if (tile < tile_end) { open_tile(tile); load_chunk(0, cur); }
+    float sc[4][CT];
+    // sWi rows >= C are zero-filled (CT rows are staged), so the class loop needs no bound check
+    auto process = [&](const float4* now, int kc) {     // convert + publish chunk kc held in `now`
+      float4 wk[CT];
+      if (do_scores) {
+#pragma unroll
+        for (int k = 0; k < CT; ++k) wk[k] = lds128(swi_u32 + static_cast<uint32_t>(k * D + kc * kChunkK + seg * 4) * 4u);
+      }
+      mbar_wait(bar(A_EMPTY + stage), phase ^ 1);
+      const uint32_t hi_tile = a_ring_u32 + stage * kChunkBytes + off0;   // shared-space addresses: STS with
+      const uint32_t lo_tile = hi_tile + kTileBytes;                       // immediate offsets
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 x = now[i];
+        if (do_scores) {
+#pragma unroll
+          for (int k = 0; k < CT; ++k) {
+            float s = sc[i][k];
+            s = fmaf(x.x, wk[k].x, s); s = fmaf(x.y, wk[k].y, s); s = fmaf(x.z, wk[k].z, s); s = fmaf(x.w, wk[k].w, s);
+            sc[i][k] = s;
+          }
+        }
+        // x = hi + lo, both bf16: hi = RN(x); lo = RN(x - hi); unpacking a bf16 pair is one shift + one mask
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
+        const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - __uint_as_float(u01 << 16), x.y - __uint_as_float(u01 & 0xffff0000u));
+        const __nv_bfloat162 l23 = __floats2bfloat162_rn(x.z - __uint_as_float(u23 << 16), x.w - __uint_as_float(u23 & 0xffff0000u));
+        sts64(hi_tile + i * 4096, u01, u23);
+        sts64(lo_tile + i * 4096, *reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+      }
+      fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (required: tested)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(A_FULL + stage));
+      if (++stage == kAStages) { stage = 0; phase ^= 1; }
+    };
     while (tile < tile_end) {
       const int my_bag = cur_bag.bag;            // this tile's bag (the load state may move on below)
       const uint32_t t_N = ld_N, t_row = ld_row;
       const long long t_rowoff = ld_rowoff;
-      float sc[4][CT];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int k = 0; k < CT; ++k) sc[i][k] = 0.f;
       const int next_tile = tile + gridDim.x;
-      for (int kc = 0; kc < nchunks; ++kc) {
-        if (kc + 1 < nchunks) load_chunk(kc + 1, nxt);
-        else if (next_tile < tile_end) { open_tile(next_tile); load_chunk(0, nxt); }
-        mbar_wait(bar(A_EMPTY + stage), phase ^ 1);
-        const uint32_t hi_tile = a_ring_u32 + stage * kChunkBytes + off0;   // shared-space addresses: STS/LDS,
-        const uint32_t lo_tile = hi_tile + kTileBytes;                       // immediates instead of 64-bit math
-        const uint32_t w_addr = swi_u32 + static_cast<uint32_t>(kc * kChunkK + seg * 4) * 4u;
-        {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 x = cur[i];
-#pragma unroll
-            for (int k = 0; k < CT; ++k)
-              if (do_scores && k < C) {
-                const float4 w = lds128(w_addr + static_cast<uint32_t>(k * D) * 4u);
-                float s = sc[i][k];
-                s = fmaf(x.x, w.x, s); s = fmaf(x.y, w.y, s); s = fmaf(x.z, w.z, s); s = fmaf(x.w, w.w, s);
-                sc[i][k] = s;
-              }
-            const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
-            const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - __low2float(h01), x.y - __high2float(h01));
-            const __nv_bfloat162 l23 = __floats2bfloat162_rn(x.z - __low2float(h23), x.w - __high2float(h23));
-            sts64(hi_tile + i * 4096, *reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-            sts64(lo_tile + i * 4096, *reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
-          }
-        }
-        fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (required: tested)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(A_FULL + stage));
-        if (++stage == kAStages) { stage = 0; phase ^= 1; }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+      // two chunks per iteration: the buffers swap roles, no register copies (nchunks is even: D % 128 == 0)
+      for (int kc = 0; kc < nchunks; kc += 2) {
+        load_chunk(kc + 1, nxt);
+        process(cur, kc);
+        if (kc + 2 < nchunks) load_chunk(kc + 2, cur);
+        else if (next_tile < tile_end) { open_tile(next_tile); load_chunk(0, cur); }
+        process(nxt, kc + 1);
       }
       // instance scores of this tile: reduce over the 16 threads (seg) that share a row; the per-class
       // arg-max key of the tile goes straight to the bag's key slot (one atomicMax per warp and class)
@@ -489,7 +498,7 @@ k_qmlp_sm100(const QmlpArgs a) {
     }
   } else {
     // ====== epilogue warps: TMEM lane quadrant = warp & 3, column half = warp >> 2 =============
-    reg_inc<kRegsEpi>();
+    // (epilogue warps stay at the launch register count, kRegsEpi)
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const int row_in_tile = (warp & 3) * 32 + lane;
     const int col0 = (warp >> 2) * 64;
@@ -617,7 +626,10 @@ k_prep_wimg2(const float* __restrict__ W1, int D, const float* __restrict__ W2, 
   }
 }
 
-inline size_t qmlp_smem_bytes(int C, int D) { return kSmemFixed + sizeof(float) * C * D + 1024; }
+inline size_t qmlp_smem_bytes(int C, int D) {   // Wi is staged with C rounded up to 1, 2, 4, 8 rows
+  const int ct = C <= 1 ? 1 : (C <= 2 ? 2 : (C <= 4 ? 4 : 8));
+  return kSmemFixed + sizeof(float) * ct * D + 1024;
+}
 inline size_t wimg_bytes(int D) { return static_cast<size_t>(D / kChunkK) * kChunkBytes + 2 * kChunkBytes; }
 inline bool qmlp_supported(const dsmil_params_t* p) {
   return p->nonlinear && p->D % (2 * kChunkK) == 0 && qmlp_smem_bytes(p->C, p->D) <= 232448;

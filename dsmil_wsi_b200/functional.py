@@ -90,7 +90,7 @@ class MILForwardFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, feats, v_input, v_mask, classes_in, Wi, bi, W1, b1, W2, b2, Wv, bv, Wf, bf):
+    def forward(ctx, want_grad, feats, v_input, v_mask, classes_in, Wi, bi, W1, b1, W2, b2, Wv, bv, Wf, bf):
         lib = _lib.load()
         ctx.set_materialize_grads(False)
         P = ParamPack(Wi, bi, W1, b1, W2, b2, Wv, bv, Wf, bf)
@@ -105,7 +105,9 @@ class MILForwardFn(torch.autograd.Function):
         if classes_in is not None:
             require_cuda(classes_in, "classes")
             cin = _f32c(classes_in.reshape(N, Cc))
-        need_grad = any(ctx.needs_input_grad)  # (grad mode is already off inside Function.forward)
+        # grad mode is already off inside Function.forward, so the caller tells us (mil_forward checks
+        # torch.is_grad_enabled()); without it the activations are not saved and Q stays in the blocked workspace
+        need_grad = bool(want_grad) and any(ctx.needs_input_grad)
         with torch.cuda.device(X.device):
             new = lambda *s: torch.empty(*s, dtype=torch.float32, device=X.device)
             classes = new(N, Cc) if cin is None else new(0, Cc)  # bag form: scores are an input, not an output
@@ -141,7 +143,7 @@ class MILForwardFn(torch.autograd.Function):
         X, xv, v_mask, sQ, sH, sV, A, B, crit, *params = ctx.saved_tensors
         P = ParamPack(*params)
         N, Cc, D = int(X.shape[0]), P.C, P.D
-        needs = ctx.needs_input_grad  # feats, v_input, v_mask, classes_in, 10 params
+        needs = ctx.needs_input_grad[1:]  # (want_grad,) feats, v_input, v_mask, classes_in, 10 params
         names = ("Wi", "bi", "W1", "b1", "W2", "b2", "Wv", "bv", "Wf", "bf")
         with torch.cuda.device(X.device):
             out = {}
@@ -161,7 +163,7 @@ class MILForwardFn(torch.autograd.Function):
                                     _ptr(crit), _ptr(dc), _ptr(dp), _ptr(dA), _ptr(dB), C.byref(G),
                                     _ptr(v_mask), _ptr(ws), ws.numel(), _stream())
             _lib.check(rc, "dsmil_backward")
-        return (gX, None, None, None, *[out[n] for n in names])
+        return (None, gX, None, None, None, *[out[n] for n in names])
 
 
 # --------------------------------------------------------------------------- instance scores alone
@@ -212,7 +214,8 @@ def instance_scores(feats: torch.Tensor, weight: torch.Tensor, bias: torch.Tenso
 def mil_forward(feats, params: Sequence[Optional[torch.Tensor]], v_input=None, v_mask=None, classes_in=None
                 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """Returns (classes, prediction_bag, A, B, crit_idx)."""
-    return MILForwardFn.apply(feats, v_input, v_mask, classes_in, *params)
+    want_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (feats, *params))
+    return MILForwardFn.apply(want_grad, feats, v_input, v_mask, classes_in, *params)
 
 
 @torch.no_grad()
