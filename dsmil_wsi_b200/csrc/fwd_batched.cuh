@@ -36,7 +36,6 @@ k_attend_b(const AttendArgs a) {
   __shared__ float sL[kAttRows][CT];
   __shared__ float sE[kAttRows][CT];
   __shared__ float s_red[8][CT];
-  __shared__ float s_m[CT], s_s[CT], s_scale[CT];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = a.C, D = a.D;
   // which bag does this CTA belong to?
@@ -58,7 +57,9 @@ k_attend_b(const AttendArgs a) {
     }
     sq[k][j] = v;
   }
-  if (tid < CT) { s_m[tid] = -INFINITY; s_s[tid] = 0.f; }
+  float run_m[CT], run_s[CT];                   // running (max, sum), replicated in every thread
+#pragma unroll
+  for (int k = 0; k < CT; ++k) { run_m[k] = -INFINITY; run_s[k] = 0.f; }
   float acc[CT][NJ][4];
 #pragma unroll
   for (int k = 0; k < CT; ++k)
@@ -73,7 +74,10 @@ k_attend_b(const AttendArgs a) {
   for (int t = cta_in_bag; t < ntiles; t += bg.nrec) {
     const long long r0 = static_cast<long long>(t) * kAttRows;
     const int rows = static_cast<int>((bg.N - r0) < kAttRows ? (bg.N - r0) : kAttRows);
-    // (a) logits
+    // (a) logits -> registers of threads 0..127 (row = tid), -inf for rows beyond the bag
+    float Lr[CT];
+#pragma unroll
+    for (int k = 0; k < CT; ++k) Lr[k] = -INFINITY;
     if (a.q_blocked) {
       // thread (row = tid & 127, column half = tid >> 7): 64 coalesced column loads, no shuffles
       const int r = tid & 127, hf = tid >> 7;
@@ -81,7 +85,7 @@ k_attend_b(const AttendArgs a) {
       float d[CT];
 #pragma unroll
       for (int k = 0; k < CT; ++k) d[k] = 0.f;
-#pragma unroll 8
+#pragma unroll 4
       for (int c = 0; c < 64; c += 4) {
         const float q0 = __ldg(qb + (c + 0) * kAttRows), q1 = __ldg(qb + (c + 1) * kAttRows);
         const float q2 = __ldg(qb + (c + 2) * kAttRows), q3 = __ldg(qb + (c + 3) * kAttRows);
@@ -96,79 +100,78 @@ k_attend_b(const AttendArgs a) {
         for (int k = 0; k < CT; ++k) sE[r][k] = d[k];          // park the upper-half partial
       }
       __syncthreads();
-      if (hf == 0) {
+      if (hf == 0 && r < rows) {
 #pragma unroll
         for (int k = 0; k < CT; ++k) {
-          float L = -INFINITY;
-          if (r < rows) {
-            L = __fdiv_rn(d[k] + sE[r][k], kScale);             // dsmil.py:56: a division by sqrt(128f)
-            if (k < C) a.A[(bg.row_off + r0 + r) * C + k] = L;
-          }
-          sL[r][k] = L;
+          Lr[k] = __fdiv_rn(d[k] + sE[r][k], kScale);          // dsmil.py:56: a division by sqrt(128f)
+          if (k < C) a.A[(bg.row_off + r0 + r) * C + k] = Lr[k];
         }
       }
-    } else
+    } else {
+      // row-major Q (training keeps it for the backward): warp w owns rows w*16 .. w*16+15
 #pragma unroll 4
-    for (int rr = 0; rr < 16; ++rr) {
-      const int r = warp * 16 + rr;
-      if (r < rows) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(a.Q + (bg.row_off + r0 + r) * kQ) + lane);
+      for (int rr = 0; rr < 16; ++rr) {
+        const int r = warp * 16 + rr;
+        if (r < rows) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(a.Q + (bg.row_off + r0 + r) * kQ) + lane);
 #pragma unroll
-        for (int k = 0; k < CT; ++k) {
-          const float4 w = *reinterpret_cast<const float4*>(&sq[k][lane * 4]);
-          float d = q.x * w.x;
-          d = fmaf(q.y, w.y, d);
-          d = fmaf(q.z, w.z, d);
-          d = fmaf(q.w, w.w, d);
-          d = warp_sum(d);
-          if (lane == 0) {
-            const float L = __fdiv_rn(d, kScale);   // dsmil.py:56: a division by sqrt(128f)
-            sL[r][k] = L;
-            if (k < C) a.A[(bg.row_off + r0 + r) * C + k] = L;
+          for (int k = 0; k < CT; ++k) {
+            const float4 w = *reinterpret_cast<const float4*>(&sq[k][lane * 4]);
+            float d = q.x * w.x;
+            d = fmaf(q.y, w.y, d);
+            d = fmaf(q.z, w.z, d);
+            d = fmaf(q.w, w.w, d);
+            d = warp_sum(d);
+            if (lane == 0) {
+              const float L = __fdiv_rn(d, kScale);
+              sL[r][k] = L;
+              if (k < C) a.A[(bg.row_off + r0 + r) * C + k] = L;
+            }
           }
         }
-      } else if (lane < CT) {
-        sL[r][lane] = -INFINITY;
       }
-    }
-    __syncthreads();
-    // (b) running max, rescale factor, exp weights, running sum
-    if (tid < CT) {
-      float mx = s_m[tid];
-      for (int r = 0; r < kAttRows; ++r) mx = fmaxf(mx, sL[r][tid]);
-      const float old = s_m[tid];
-      s_scale[tid] = (old == -INFINITY) ? 0.f : expf(old - mx);
-      s_m[tid] = mx;
-    }
-    __syncthreads();
-    {
-      float e[CT];
+      __syncthreads();
+      if (tid < rows) {
 #pragma unroll
-      for (int k = 0; k < CT; ++k) {
-        float ev = 0.f;
-        if (tid < kAttRows) {
-          const float L = sL[tid][k];
-          ev = (L == -INFINITY) ? 0.f : expf(L - s_m[k]);
-          sE[tid][k] = ev;
-        }
-        e[k] = warp_sum(ev);
-        if (lane == 0) s_red[warp][k] = e[k];
+        for (int k = 0; k < CT; ++k) Lr[k] = sL[tid][k];
       }
     }
+    // (b) tile max (warp shuffles + 4 partials), running max / rescale, exp weights, running sum --
+    //     every thread derives the same (m, s) from shared partials: no single-thread phases
+#pragma unroll
+    for (int k = 0; k < CT; ++k) {
+      const float v = warp_max(Lr[k]);
+      if (lane == 0) s_red[warp][k] = v;       // warps 4..7 hold no rows: -inf
+    }
     __syncthreads();
-    if (tid < CT) {
-      float s = s_s[tid] * s_scale[tid];
-      for (int w = 0; w < 4; ++w) s += s_red[w][tid];    // rows live in threads 0..127 == warps 0..3
-      s_s[tid] = s;
+    float mnew[CT], scl[CT], ev[CT];
+#pragma unroll
+    for (int k = 0; k < CT; ++k) {
+      float mx = fmaxf(fmaxf(s_red[0][k], s_red[1][k]), fmaxf(s_red[2][k], s_red[3][k]));
+      mnew[k] = fmaxf(run_m[k], mx);
+      scl[k] = (run_m[k] == -INFINITY) ? 0.f : expf(run_m[k] - mnew[k]);
+      ev[k] = (Lr[k] == -INFINITY) ? 0.f : expf(Lr[k] - mnew[k]);
+      if (tid < kAttRows) sE[tid][k] = ev[k];
+    }
+    __syncthreads();                           // s_red reads done, sE visible
+#pragma unroll
+    for (int k = 0; k < CT; ++k) {
+      const float v = warp_sum(ev[k]);
+      if (lane == 0) s_red[warp][k] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < CT; ++k) {
+      run_s[k] = run_s[k] * scl[k] + ((s_red[0][k] + s_red[1][k]) + (s_red[2][k] + s_red[3][k]));
+      run_m[k] = mnew[k];
     }
     // (c) weighted feature sum: this thread takes rows of its parity, float4 columns c4 + 128*j
 #pragma unroll
     for (int k = 0; k < CT; ++k) {
-      const float sc = s_scale[k];
 #pragma unroll
       for (int j = 0; j < NJ; ++j)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[k][j][e] *= sc;
+        for (int e = 0; e < 4; ++e) acc[k][j][e] *= scl[k];
     }
     const float* xb = bg.X + r0 * D;
 #pragma unroll 4
@@ -226,7 +229,11 @@ k_attend_b(const AttendArgs a) {
           }
         }
   }
-  if (tid < C) { recp[tid] = s_m[tid]; recp[C + tid] = s_s[tid]; }
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < CT; ++k)
+      if (k < C) { recp[k] = run_m[k]; recp[C + k] = run_s[k]; }
+  }
 }
 
 struct FinalizeArgs {
