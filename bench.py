@@ -213,7 +213,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     from dsmil_wsi_b200 import _lib
     from dsmil_wsi_b200.pipeline import HostBagPipeline
-    from dsmil_wsi_b200.sharded import CudaShardOps, milnet_params, sharded_forward_bags
+    from dsmil_wsi_b200.sharded import (CudaShardBagOps, CudaShardOps, milnet_params, sharded_forward_bags,
+                                        sharded_forward_bags_batched)
     lib = _lib.load()
 
     p = make_params()
@@ -222,13 +223,23 @@ def run_ours(args):
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     bags = [torch.rand(NBAG, D, generator=g, device=dev) for _ in range(nb)]   # this rank's rows of each bag
     offsets = [rank * NBAG] * nb
-    ops = CudaShardOps(milnet_params(net)) if world > 1 else None
+    ops = bops = None
+    if world > 1:
+        if CudaShardBagOps.supported(milnet_params(net)):
+            bops = CudaShardBagOps(milnet_params(net))
+        else:
+            ops = CudaShardOps(milnet_params(net))
+
+    def sharded_step(xs):
+        if bops is not None:
+            return sharded_forward_bags_batched(bops, xs, offsets)
+        return sharded_forward_bags(ops, xs, offsets)
 
     def step():
         with torch.no_grad():
             if world == 1:
                 return net.forward_bags(bags)
-            return sharded_forward_bags(ops, bags, offsets)
+            return sharded_step(bags)
 
     def barrier():
         if world > 1:
@@ -311,7 +322,7 @@ def run_ours(args):
             with torch.no_grad():
                 for s, h in zip(slots, host):
                     s.copy_(h, non_blocking=True)
-                outs = sharded_forward_bags(ops, slots, offsets)
+                outs = sharded_step(slots)
                 return [tuple(t.cpu() for t in o[:4]) for o in outs]
         e2e_step(); barrier()
         t0 = time.perf_counter()

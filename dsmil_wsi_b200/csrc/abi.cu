@@ -395,13 +395,51 @@ static int forward_bags_impl(const dsmil_params_t* p, const float* const* Xs, co
     if ((rc = sm100::launch_qmlp(p, w.table, b0, b1 - b0, t0, t1 - t0, classes_in ? nullptr : classes, w.keys, Q,
                                  save_H1, img, num_sms(), st, q_blocked)))
       return rc;
-    sm100::AttendArgs aa{w.table, b0, b1 - b0, r0, D, C, Q, q_blocked, w.keys, A, w.recs};
+    sm100::AttendArgs aa{w.table, b0, b1 - b0, r0, D, C, Q, q_blocked, w.keys, A, w.recs, nullptr};
     if ((rc = sm100::launch_attend_b(aa, r1 - r0, st))) return rc;
     sm100::FinalizeArgs fa{w.table, b0, D, C, w.recs, w.keys, p->Wf, p->bf, A, B, pred,
-                           reinterpret_cast<long long*>(crit), w.pred_part, w.counters};
+                           reinterpret_cast<long long*>(crit), w.pred_part, w.counters, nullptr, 0, 0};
     if ((rc = sm100::launch_finalize_b(fa, b1 - b0, st))) return rc;
     b0 = b1;
   }
+  return 0;
+}
+
+
+// ---- row-sharded BATCH of bags (one call per phase for all bags; two all-gathers per step) --------------
+struct ShardBagsWs {
+  BagsWs base;
+  long long* row_offsets;   // [nb] device copy
+  float* qmax;              // [nb][C][128]
+  size_t bytes;
+};
+static ShardBagsWs carve_shard_bags(const dsmil_params_t* p, const int64_t* Ns, int nb, void* ws, size_t cap, bool* ok) {
+  ShardBagsWs s;
+  s.base = carve_bags(p, Ns, nb, true, ws, cap, ok);
+  Carver c(ws, cap);
+  c.off = s.base.bytes;
+  s.row_offsets = c.take<long long>(nb);
+  s.qmax = c.take<float>(static_cast<size_t>(nb) * p->C * kQ);
+  s.bytes = c.off;
+  *ok = c.ok();
+  return s;
+}
+static int build_table(const float* const* Xs, const int64_t* Ns, int nb, std::vector<sm100::BagDev>& tbl, int* tiles,
+                       int* recs) {
+  long long row = 0;
+  int tile = 0, rec = 0;
+  tbl.resize(nb);
+  for (int b = 0; b < nb; ++b) {
+    DSMIL_REQUIRE(Ns[b] >= 1 && Ns[b] < 0xffffffffll && Xs[b], "bag %d: empty or NULL (sharded batches need >= 1 row per rank)", b);
+    DSMIL_REQUIRE((reinterpret_cast<uintptr_t>(Xs[b]) & 15) == 0, "bag %d: features must be 16-byte aligned", b);
+    const int nrec = recs_for_bag(Ns[b]);
+    tbl[b] = sm100::BagDev{Xs[b], Ns[b], row, tile, rec, nrec, 0};
+    row += Ns[b];
+    tile += static_cast<int>((Ns[b] + sm100::kTileM - 1) / sm100::kTileM);
+    rec += nrec;
+  }
+  *tiles = tile;
+  *recs = rec;
   return 0;
 }
 
@@ -724,6 +762,80 @@ int dsmil_instance_scores_backward(const dsmil_params_t* p, const float* X, int6
     DSMIL_LAUNCH_OK("k_bwd_dx_extra");
   }
   return 0;
+}
+
+// ---- sharded batch ABI ---------------------------------------------------------------------------
+int dsmil_shard_bags_supported(const dsmil_params_t* p) {
+  return (p && p->C >= 1 && p->C <= DSMIL_MAX_C && p->D >= 1 && p->D <= DSMIL_MAX_D && use_sm100(p) &&
+          sm100::batched_supported(p)) ? 1 : 0;
+}
+size_t dsmil_shard_bags_workspace_bytes(const dsmil_params_t* p, const int64_t* Ns, int32_t nb) {
+  if (!dsmil_shard_bags_supported(p) || !Ns || nb < 1) return 0;
+  bool ok;
+  return carve_shard_bags(p, Ns, nb, nullptr, 0, &ok).bytes;
+}
+int dsmil_shard_bags_phase1(const dsmil_params_t* p, const float* const* Xs, const int64_t* Ns, int32_t nb,
+                            const int64_t* row_offsets, float* classes, float* cand_recs, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  int rc = check_params(p, true);
+  if (rc) return rc;
+  DSMIL_REQUIRE(dsmil_shard_bags_supported(p), "shape not supported by the batched tensor-core path");
+  DSMIL_REQUIRE(Xs && Ns && nb >= 1 && row_offsets && classes && cand_recs, "NULL pointer or nb < 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bool ok;
+  ShardBagsWs w = carve_shard_bags(p, Ns, nb, workspace, workspace_bytes, &ok);
+  if (!workspace || !ok) { set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes); return DSMIL_ERR_WORKSPACE; }
+  std::vector<sm100::BagDev> tbl;
+  int tiles = 0, recs = 0;
+  if ((rc = build_table(Xs, Ns, nb, tbl, &tiles, &recs))) return rc;
+  DSMIL_CUDA_OK(cudaMemcpyAsync(w.base.table, tbl.data(), sizeof(sm100::BagDev) * nb, cudaMemcpyHostToDevice, st));
+  DSMIL_CUDA_OK(cudaMemcpyAsync(w.row_offsets, row_offsets, sizeof(long long) * nb, cudaMemcpyHostToDevice, st));
+  DSMIL_CUDA_OK(cudaMemsetAsync(w.base.keys, 0, sizeof(unsigned long long) * (kMaxC + 1) * nb, st));
+  uint8_t* img = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(w.base.wimg) + 1023) & ~uintptr_t(1023));
+  if ((rc = sm100::launch_prep_wimg(p, img, st))) return rc;
+  if ((rc = sm100::launch_qmlp(p, w.base.table, 0, nb, 0, tiles, classes, w.base.keys, w.base.Q, nullptr, img, num_sms(), st, 1)))
+    return rc;
+  sm100::k_gather_cand_b<<<dim3(p->C, nb), kQ, 0, st>>>(w.base.table, w.base.keys, classes, w.base.Q, 1, w.row_offsets, p->C,
+                                                        cand_recs);
+  DSMIL_LAUNCH_OK("k_gather_cand_b");
+  return 0;
+}
+int dsmil_shard_bags_phase2(const dsmil_params_t* p, const float* const* Xs, const int64_t* Ns, int32_t nb,
+                            const float* cands_all, int32_t G, float* A, int64_t* crit_idx, float* recs_out,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_params(p, true);
+  if (rc) return rc;
+  DSMIL_REQUIRE(dsmil_shard_bags_supported(p) && Xs && Ns && nb >= 1 && cands_all && G >= 1 && A && crit_idx && recs_out,
+                "bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bool ok;
+  ShardBagsWs w = carve_shard_bags(p, Ns, nb, workspace, workspace_bytes, &ok);
+  if (!workspace || !ok) { set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes); return DSMIL_ERR_WORKSPACE; }
+  std::vector<sm100::BagDev> tbl;
+  int tiles = 0, recs = 0;
+  if ((rc = build_table(Xs, Ns, nb, tbl, &tiles, &recs))) return rc;   // the device table was written by phase 1
+  sm100::k_merge_cand_b<<<dim3(p->C, nb), kQ, 0, st>>>(cands_all, G, nb, p->C, w.qmax, reinterpret_cast<long long*>(crit_idx));
+  DSMIL_LAUNCH_OK("k_merge_cand_b");
+  sm100::AttendArgs aa{w.base.table, 0, nb, 0, p->D, p->C, w.base.Q, 1, w.base.keys, A, w.base.recs, w.qmax};
+  if ((rc = sm100::launch_attend_b(aa, recs, st))) return rc;
+  sm100::FinalizeArgs fa{w.base.table, 0, p->D, p->C, w.base.recs, w.base.keys, p->Wf, p->bf, A, nullptr, nullptr, nullptr,
+                         w.base.pred_part, w.base.counters, recs_out, 0, 0};
+  return sm100::launch_finalize_b(fa, nb, st);
+}
+int dsmil_shard_bags_phase3(const dsmil_params_t* p, const float* const* Xs, const int64_t* Ns, int32_t nb,
+                            const float* recs_all, int32_t G, float* A, float* B, float* pred, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  int rc = check_params(p, true);
+  if (rc) return rc;
+  DSMIL_REQUIRE(dsmil_shard_bags_supported(p) && Xs && Ns && nb >= 1 && recs_all && G >= 1 && G <= sm100::kMaxRecPerBag && A && B && pred,
+                "bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bool ok;
+  ShardBagsWs w = carve_shard_bags(p, Ns, nb, workspace, workspace_bytes, &ok);
+  if (!workspace || !ok) { set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes); return DSMIL_ERR_WORKSPACE; }
+  sm100::FinalizeArgs fa{w.base.table, 0, p->D, p->C, recs_all, w.base.keys, p->Wf, p->bf, A, B, pred, nullptr,
+                         w.base.pred_part, w.base.counters, nullptr, G, nb};
+  return sm100::launch_finalize_b(fa, nb, st);
 }
 
 }  // extern "C"

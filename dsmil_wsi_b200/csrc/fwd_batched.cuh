@@ -25,6 +25,7 @@ struct AttendArgs {
   const unsigned long long* keys;  // [nbags][kMaxC]
   float* A;                 // packed [sumN,C]: receives the raw logits here
   float* recs;              // [total records][rec_floats(C,D)]
+  const float* qmax_ext;    // sharded: [nbags][C][128] merged critical queries (NULL: gather from Q via keys)
 };
 
 // CT = classes rounded up to 1,2,4; NJ = float4 column groups per thread (D <= 512*NJ)
@@ -50,7 +51,9 @@ k_attend_b(const AttendArgs a) {
   for (int i = tid; i < CT * kQ; i += 256) {
     const int k = i / kQ, j = i % kQ;
     float v = 0.f;
-    if (k < C) {
+    if (k < C && a.qmax_ext != nullptr) {
+      v = a.qmax_ext[(static_cast<size_t>(bag) * C + k) * kQ + j];
+    } else if (k < C) {
       const long long row = key_row(a.keys[static_cast<size_t>(bag) * kMaxC + k]);
       v = a.q_blocked ? a.Q[static_cast<size_t>(bg.tile_off + row / kAttRows) * (kAttRows * kQ) + j * kAttRows + (row % kAttRows)]
                       : a.Q[(bg.row_off + row) * kQ + j];
@@ -250,6 +253,11 @@ struct FinalizeArgs {
   long long* crit;  // [nbags, C] or NULL
   float* pred_part;        // [nbags][kFinSlices][kMaxC] partial bag logits
   unsigned int* counters;  // [nbags] arrival counters (zeroed by the host before the batch)
+  // sharded use: (1) emit != NULL: combine this rank's records of each bag into ONE unnormalised record
+  // emit[bag] = (M, S, sum Bp*w) and stop (no A / B / logits);  (2) ext_P > 0: the records of bag b are the
+  // ext_P per-rank records at recs[(p * ext_nb + b) * stride] (an all-gather result), not the bag table's.
+  float* emit;
+  int ext_P, ext_nb;
 };
 
 constexpr int kFinSlices = 8;
@@ -270,25 +278,27 @@ k_finalize_b(const FinalizeArgs a) {
   const int bag = a.bag0 + blockIdx.y;
   const BagDev bg = a.bags[bag];
   const size_t rstride = rec_floats(C, D);
-  const float* recs = a.recs + static_cast<size_t>(bg.rec_off) * rstride;
-  const int P = bg.nrec;
+  const bool ext = a.ext_P > 0;
+  const float* recs = ext ? a.recs + static_cast<size_t>(bag) * rstride : a.recs + static_cast<size_t>(bg.rec_off) * rstride;
+  const size_t pstride = ext ? rstride * a.ext_nb : rstride;     // distance between consecutive records of the bag
+  const int P = ext ? a.ext_P : bg.nrec;
   // (M, S): thread (k, j) scans records j, j+32, ... ; fixed-order combine
   for (int k = warp; k < C; k += 8) {
     float m = -INFINITY;
-    for (int p = lane; p < P; p += 32) m = fmaxf(m, recs[p * rstride + k]);
+    for (int p = lane; p < P; p += 32) m = fmaxf(m, recs[p * pstride + k]);
     m = warp_max(m);
     float s = 0.f;
     for (int p = lane; p < P; p += 32) {
-      const float mp = recs[p * rstride + k];
+      const float mp = recs[p * pstride + k];
       const float w = (mp == -INFINITY) ? 0.f : expf(mp - m);
       sw[p][k] = w;
-      s = fmaf(recs[p * rstride + C + k], w, s);
+      s = fmaf(recs[p * pstride + C + k], w, s);
     }
     s = warp_sum(s);
     if (lane == 0) { sM[k] = m; sS[k] = s; }
   }
   __syncthreads();
-  {  // normalise this slice's rows of A
+  if (a.emit == nullptr) {  // normalise this slice's rows of A
     const long long total = bg.N * C;
     const long long per = (total + gridDim.x - 1) / gridDim.x;
     const long long lo = per * blockIdx.x, hi = (lo + per) < total ? (lo + per) : total;
@@ -317,21 +327,30 @@ k_finalize_b(const FinalizeArgs a) {
       for (; p + 14 < P; p += 16) {   // 8 independent loads in flight
         float v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = col[static_cast<size_t>(p + 2 * u) * rstride];
+        for (int u = 0; u < 8; ++u) v[u] = col[static_cast<size_t>(p + 2 * u) * pstride];
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc = fmaf(v[u], sw[p + 2 * u][k], acc);
       }
-      for (; p < P; p += 2) acc = fmaf(col[static_cast<size_t>(p) * rstride], sw[p][k], acc);
+      for (; p < P; p += 2) acc = fmaf(col[static_cast<size_t>(p) * pstride], sw[p][k], acc);
     }
     if (par == 1) s_part[tid & 127] = acc;
     __syncthreads();
-    if (par == 0 && e < e_hi) {
+    if (par == 0 && e < e_hi && a.emit != nullptr) {
+      a.emit[static_cast<size_t>(bag) * rstride + 2 * C + e] = acc + s_part[tid];
+    } else if (par == 0 && e < e_hi) {
       const int k = e / D;
       const float b = __fdiv_rn(acc + s_part[tid], sS[k]);
       a.B[static_cast<size_t>(bag) * CD + e] = b;
       for (int kk = 0; kk < C; ++kk) ppart[kk] = fmaf(__ldg(a.Wf + static_cast<size_t>(kk) * CD + e), b, ppart[kk]);
     }
     __syncthreads();
+  }
+  if (a.emit != nullptr) {
+    if (blockIdx.x == 0 && tid < C) {
+      a.emit[static_cast<size_t>(bag) * rstride + tid] = sM[tid];
+      a.emit[static_cast<size_t>(bag) * rstride + C + tid] = sS[tid];
+    }
+    return;
   }
   // partial Conv1d logits of this slice (fixed reduction order inside the CTA)
   for (int kk = 0; kk < C; ++kk) {
@@ -358,6 +377,60 @@ k_finalize_b(const FinalizeArgs a) {
     a.pred[static_cast<size_t>(bag) * C + tid] = s + __ldg(a.bf + tid);
     if (a.crit) a.crit[static_cast<size_t>(bag) * C + tid] = key_row(a.keys[static_cast<size_t>(bag) * kMaxC + tid]);
   }
+}
+
+// Candidate record of every bag of this rank (layout of fwd_kernels.cuh: idx[C] int64 | score[C] | qrow[C,128]).
+// grid = (C, nb), 128 threads.  row_offsets[b] = global index of the bag's first local row.
+__global__ void __launch_bounds__(128)
+k_gather_cand_b(const BagDev* __restrict__ bags, const unsigned long long* __restrict__ keys,
+                const float* __restrict__ classes, const float* __restrict__ Q, int q_blocked,
+                const long long* __restrict__ row_offsets, int C, float* __restrict__ cands) {
+  const int k = blockIdx.x, bag = blockIdx.y;
+  const BagDev bg = bags[bag];
+  float* cand = cands + static_cast<size_t>(bag) * cand_floats(C);
+  long long* idx = reinterpret_cast<long long*>(cand);
+  float* score = cand + 2 * C;
+  float* qrow = cand + 3 * C + static_cast<size_t>(k) * kQ;
+  const unsigned long long key = keys[static_cast<size_t>(bag) * kMaxC + k];
+  if (bg.N <= 0 || key == 0ull) {
+    if (threadIdx.x == 0) { idx[k] = INT64_MAX; score[k] = -INFINITY; }
+    qrow[threadIdx.x] = 0.f;
+    return;
+  }
+  const long long row = key_row(key);
+  if (threadIdx.x == 0) {
+    idx[k] = row + row_offsets[bag];
+    score[k] = classes[(bg.row_off + row) * C + k];
+  }
+  qrow[threadIdx.x] = q_blocked
+      ? Q[static_cast<size_t>(bg.tile_off + row / kAttRows) * (kAttRows * kQ) + threadIdx.x * kAttRows + (row % kAttRows)]
+      : Q[(bg.row_off + row) * kQ + threadIdx.x];
+}
+
+// Winner per (bag, class) over the G ranks' candidate records cands[g][bag]; grid = (C, nb), 128 threads.
+__global__ void __launch_bounds__(128)
+k_merge_cand_b(const float* __restrict__ cands, int G, int nb, int C, float* __restrict__ qmax,
+               long long* __restrict__ crit) {
+  const int k = blockIdx.x, bag = blockIdx.y;
+  const size_t stride = cand_floats(C);
+  int best_g = -1;
+  uint32_t best_key = 0;
+  long long best_idx = INT64_MAX;
+  for (int g = 0; g < G; ++g) {
+    const float* rec = cands + (static_cast<size_t>(g) * nb + bag) * stride;
+    const long long gi = reinterpret_cast<const long long*>(rec)[k];
+    if (gi == INT64_MAX) continue;
+    const uint32_t key = ordered_key(rec[2 * C + k]);
+    if (best_g < 0 || key > best_key || (key == best_key && gi < best_idx)) { best_g = g; best_key = key; best_idx = gi; }
+  }
+  float* out = qmax + (static_cast<size_t>(bag) * C + k) * kQ;
+  if (best_g < 0) {
+    if (threadIdx.x == 0) crit[static_cast<size_t>(bag) * C + k] = -1;
+    out[threadIdx.x] = 0.f;
+    return;
+  }
+  if (threadIdx.x == 0) crit[static_cast<size_t>(bag) * C + k] = best_idx;
+  out[threadIdx.x] = cands[(static_cast<size_t>(best_g) * nb + bag) * stride + 3 * C + static_cast<size_t>(k) * kQ + threadIdx.x];
 }
 
 inline bool batched_supported(const dsmil_params_t* p) {

@@ -107,6 +107,88 @@ class CudaShardOps:
         return A, B, pred
 
 
+class CudaShardBagOps:
+    """Batched form of the three local phases (dsmil_shard_bags_*): one library call per phase for ALL bags of
+    a step, tensor-core path.  The workspace lives across the phases of one step."""
+
+    def __init__(self, params: Sequence[Optional[torch.Tensor]]):
+        self.lib = _lib.load()
+        self.P = Fn.ParamPack(*params)
+        self.device = self.P.device
+        if not self.lib.dsmil_shard_bags_supported(self.P.ref):
+            raise RuntimeError("dsmil_b200: this (D, C, q/v variant) has no batched sharded path; use CudaShardOps")
+
+    @staticmethod
+    def supported(params) -> bool:
+        P = Fn.ParamPack(*params)
+        return bool(_lib.load().dsmil_shard_bags_supported(P.ref))
+
+    def begin(self, X_locals: Sequence[torch.Tensor], row_offsets: Sequence[int]):
+        P = self.P
+        self.xs = [Fn._check_feats(x, P.D) for x in X_locals]
+        self.nb = len(self.xs)
+        self.Ns = [int(x.shape[0]) for x in self.xs]
+        if min(self.Ns) < 1:
+            raise ValueError("sharded batches need at least one local row per bag on every rank")
+        self.c_N = (C.c_int64 * self.nb)(*self.Ns)
+        self.c_X = (C.c_void_p * self.nb)(*[x.data_ptr() for x in self.xs])
+        self.c_off = (C.c_int64 * self.nb)(*[int(o) for o in row_offsets])
+        self.total = sum(self.Ns)
+        with torch.cuda.device(self.device):
+            self.ws = Fn._workspace(self.lib.dsmil_shard_bags_workspace_bytes(P.ref, self.c_N, self.nb), self.device)
+        self.cand_f = int(self.lib.dsmil_cand_floats(P.C))
+        self.rec_f = int(self.lib.dsmil_rec_floats(P.C, P.D))
+
+    def new(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def phase1(self):
+        P = self.P
+        with torch.cuda.device(self.device):
+            self.classes = self.new(self.total, P.C)
+            cand = self.new(self.nb, self.cand_f)
+            rc = self.lib.dsmil_shard_bags_phase1(P.ref, self.c_X, self.c_N, self.nb, self.c_off, Fn._ptr(self.classes),
+                                                  Fn._ptr(cand), Fn._ptr(self.ws), self.ws.numel(), Fn._stream())
+            _lib.check(rc, "dsmil_shard_bags_phase1")
+        return cand
+
+    def phase2(self, cands_all: torch.Tensor, G: int):
+        P = self.P
+        with torch.cuda.device(self.device):
+            self.A = self.new(self.total, P.C)
+            self.crit = self.new(self.nb, P.C, dtype=torch.int64)
+            recs = self.new(self.nb, self.rec_f)
+            rc = self.lib.dsmil_shard_bags_phase2(P.ref, self.c_X, self.c_N, self.nb, Fn._ptr(cands_all), G, Fn._ptr(self.A),
+                                                  Fn._ptr(self.crit), Fn._ptr(recs), Fn._ptr(self.ws), self.ws.numel(),
+                                                  Fn._stream())
+            _lib.check(rc, "dsmil_shard_bags_phase2")
+        return recs
+
+    def phase3(self, recs_all: torch.Tensor, G: int):
+        P = self.P
+        with torch.cuda.device(self.device):
+            B, pred = self.new(self.nb, P.C, P.D), self.new(self.nb, P.C)
+            rc = self.lib.dsmil_shard_bags_phase3(P.ref, self.c_X, self.c_N, self.nb, Fn._ptr(recs_all), G, Fn._ptr(self.A),
+                                                  Fn._ptr(B), Fn._ptr(pred), Fn._ptr(self.ws), self.ws.numel(), Fn._stream())
+            _lib.check(rc, "dsmil_shard_bags_phase3")
+        outs, row = [], 0
+        for b, n in enumerate(self.Ns):
+            outs.append((self.classes[row:row + n], pred[b:b + 1], self.A[row:row + n], B[b:b + 1], self.crit[b]))
+            row += n
+        return outs
+
+
+@torch.no_grad()
+def sharded_forward_bags_batched(bops: "CudaShardBagOps", X_locals, row_offsets, group=None):
+    """sharded_forward_bags on the batched ABI: 3 library calls + 2 all-gathers per step, whatever the batch."""
+    bops.begin(X_locals, row_offsets)
+    cand = bops.phase1()
+    cands_all, G = _all_gather(cand.view(-1), group)        # exchange 1: [G][nb][cand]
+    recs = bops.phase2(cands_all, G)
+    recs_all, G = _all_gather(recs.view(-1), group)         # exchange 2: [G][nb][rec]
+    return bops.phase3(recs_all, G)
+
+
 def _all_gather(rec: torch.Tensor, group) -> Tuple[torch.Tensor, int]:
     import torch.distributed as dist
     G = dist.get_world_size(group)

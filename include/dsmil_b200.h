@@ -163,6 +163,25 @@ int dsmil_shard_merge_partials(int32_t C, int32_t Dv, const float* recs, int32_t
 int dsmil_shard_phase3(const dsmil_params_t* p, int64_t N_local, const float* rec_global,
                        float* A, float* B, float* pred, void* stream);
 
+/* The same three phases for a BATCH of row-sharded bags (tensor-core path; dsmil_shard_bags_supported):
+ * every rank passes its local rows of all nb bags; records are packed per bag so that a whole step costs
+ * two all-gathers.  Xs/Ns/row_offsets are host arrays; the workspace must be the same buffer in all three
+ * calls (it carries Q, the bag table and the per-tile partial records between the phases).
+ *   phase1 -> classes (packed), cand_recs [nb][dsmil_cand_floats(C)]
+ *   phase2 (cands_all [G][nb][cand]) -> A (logits, packed), crit_idx [nb][C], recs_out [nb][dsmil_rec_floats(C,D)]
+ *   phase3 (recs_all  [G][nb][rec])  -> A normalised, B [nb][C][D], pred [nb][C] */
+int dsmil_shard_bags_supported(const dsmil_params_t* p);
+size_t dsmil_shard_bags_workspace_bytes(const dsmil_params_t* p, const int64_t* Ns, int32_t nb);
+int dsmil_shard_bags_phase1(const dsmil_params_t* p, const float* const* Xs, const int64_t* Ns, int32_t nb,
+                            const int64_t* row_offsets, float* classes, float* cand_recs,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int dsmil_shard_bags_phase2(const dsmil_params_t* p, const float* const* Xs, const int64_t* Ns, int32_t nb,
+                            const float* cands_all, int32_t G, float* A, int64_t* crit_idx, float* recs_out,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int dsmil_shard_bags_phase3(const dsmil_params_t* p, const float* const* Xs, const int64_t* Ns, int32_t nb,
+                            const float* recs_all, int32_t G, float* A, float* B, float* pred,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

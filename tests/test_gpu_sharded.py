@@ -86,3 +86,48 @@ def test_nccl_two_ranks():
         o = ret[r]
         assert np.array_equal(o["crit"], t.idx)
         assert rel_to_max(o["A"], t.A[o["lo"]:o["hi"]]) < 2e-5 and rel_to_max(o["B"], t.B) < 1e-5
+
+
+def test_batched_sharded_phases_single_rank_and_virtual():
+    """dsmil_shard_bags_*: (a) G = 1 reproduces forward_bags; (b) two logical ranks on one device, records
+    concatenated by hand in all-gather order [G][nb][rec], reproduce the unsharded bags and the oracle."""
+    from dsmil_wsi_b200.sharded import CudaShardBagOps, milnet_params, shard_bounds
+    p = orc.random_params(512, 2, 77, scale=2.0)
+    net = build_net(p).eval()
+    sizes = [700, 129, 4000]
+    Xs = [orc.synthetic_bag(n, 512, 900 + i, "uniform") for i, n in enumerate(sizes)]
+    xs = [torch.from_numpy(x).cuda() for x in Xs]
+    with torch.no_grad():
+        ref = net.forward_bags(xs)
+    params = milnet_params(net)
+    # (a) one rank
+    b1 = CudaShardBagOps(params)
+    b1.begin(xs, [0] * len(xs))
+    cand = b1.phase1()
+    recs = b1.phase2(cand.view(-1), 1)
+    out = b1.phase3(recs.view(-1), 1)
+    for o, r in zip(out, ref):
+        assert torch.equal(o[0], r[0])
+        assert rel_to_max(_np(o[2]), _np(r[2])) < 2e-6 and rel_to_max(_np(o[3]), _np(r[3])) < 2e-6
+        assert rel_to_max(_np(o[1]), _np(r[1])) < 1e-5
+    # (b) two logical ranks
+    G = 2
+    ranks = []
+    for g in range(G):
+        bo = CudaShardBagOps(params)
+        loc, offs = [], []
+        for x in xs:
+            lo, hi = shard_bounds(x.shape[0], G)[g]
+            loc.append(x[lo:hi].contiguous()); offs.append(lo)
+        bo.begin(loc, offs)
+        ranks.append(bo)
+    cands = torch.cat([bo.phase1().view(-1) for bo in ranks])
+    recs = torch.cat([bo.phase2(cands, G).view(-1) for bo in ranks])
+    outs = [bo.phase3(recs, G) for bo in ranks]
+    for b, (X, r) in enumerate(zip(Xs, ref)):
+        t = orc.forward(X, p)
+        A = torch.cat([outs[g][b][2] for g in range(G)])
+        assert np.array_equal(_np(outs[0][b][4]), t.idx) and np.array_equal(_np(outs[1][b][4]), t.idx)
+        assert rel_to_max(_np(A), t.A) < 2e-5 and rel_to_max(_np(outs[0][b][3]), t.B) < 1e-5
+        assert torch.equal(outs[0][b][3], outs[1][b][3]) and torch.equal(outs[0][b][1], outs[1][b][1])
+        assert rel_to_max(_np(A), _np(r[2])) < 2e-6
