@@ -66,17 +66,19 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the warp is parked by the hardware until the phase flips (or ~20 us pass)
+// instead of burning issue slots in a poll loop -- the spinning roles share schedulers with the converters.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t sleep_ns = 0) {
+  (void)sleep_ns;
   uint32_t done = 0, spins = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
     if (done) break;
-    if (sleep_ns) __nanosleep(sleep_ns);
-    if (++spins > kSpinLimit) __trap();  // a protocol bug must not hang the GPU
+    if (++spins > (1u << 20)) __trap();  // ~20 s: a protocol bug must not hang the GPU
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
