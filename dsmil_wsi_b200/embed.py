@@ -1,0 +1,158 @@
+"""The patch-embedding loop (reference compute_feats.py:19-82), B200-side re-design.
+
+Reference loop per bag: DataLoader(batch 128, 4 workers: PIL open + VF.to_tensor) -> `.float().cuda()`
+(synchronous, pageable, 77 MB per batch) -> `i_classifier(patches)` -> `.cpu().numpy()` (a sync per batch)
+-> Python list -> DataFrame.to_csv('%.4f').
+
+Here:
+  * decode stays on the host (PIL, thread pool) but patches cross PCIe as **uint8 HWC** from pinned, reused
+    staging buffers (19 MB per 128-patch batch instead of 77 MB), two batches in flight on a copy stream;
+  * uint8 -> fp32 CHW / 255 is `dsmil_patches_u8_to_f32` on the device (bit-identical to VF.to_tensor);
+  * the backbone is the caller's module (torchvision ResNet via cuDNN -- library code, as in the reference);
+    the instance classifier head is `dsmil_instance_scores` (our kernel) through IClassifier;
+  * features stay on the device for the whole bag: ONE D2H per bag, or none when `sink` hands the bag
+    straight to the aggregator (`milnet.b_classifier`, `MILNet.forward_bags`);
+  * the CSV wire format of the reference (`header 0..D-1`, '%.4f', no index) is written by `write_bag_csv`.
+The function signature mirrors compute_feats.compute_feats(args, bags_list, i_classifier, save_path, magnification).
+"""
+from __future__ import annotations
+
+import glob
+import os
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import functional as Fn
+
+
+def list_patches(bag_dir: str, magnification: str = "single") -> List[str]:
+    """compute_feats.py:64-68: jpg + jpeg of the bag folder ('high': one level deeper)."""
+    if magnification in ("single", "low"):
+        return glob.glob(os.path.join(bag_dir, "*.jpg")) + glob.glob(os.path.join(bag_dir, "*.jpeg"))
+    if magnification == "high":
+        return (glob.glob(os.path.join(bag_dir, "*" + os.sep + "*.jpg")) +
+                glob.glob(os.path.join(bag_dir, "*" + os.sep + "*.jpeg")))
+    raise ValueError(f"magnification {magnification!r} not handled here (tree mode is a later row, SURVEY 8f-4)")
+
+
+def _decode_u8(path: str) -> np.ndarray:
+    from PIL import Image
+    with Image.open(path) as im:
+        a = np.asarray(im.convert("RGB") if im.mode != "RGB" else im, dtype=np.uint8)
+    return np.array(a, copy=True) if not a.flags.writeable else a  # HWC uint8 (writable: torch.from_numpy)
+
+
+def patches_to_float(u8_hwc: torch.Tensor) -> torch.Tensor:
+    """uint8 [B,H,W,C] (CUDA) -> float32 [B,C,H,W] = x / 255 (== VF.to_tensor per image), on the device."""
+    Fn.require_cuda(u8_hwc, "patches")
+    if u8_hwc.dtype != torch.uint8 or u8_hwc.dim() != 4:
+        raise TypeError("patches_to_float expects a uint8 [B,H,W,C] tensor")
+    u8_hwc = u8_hwc.contiguous()
+    B, H, W, Cc = (int(s) for s in u8_hwc.shape)
+    with torch.cuda.device(u8_hwc.device):
+        out = torch.empty(B, Cc, H, W, dtype=torch.float32, device=u8_hwc.device)
+        _lib.check(_lib.load().dsmil_patches_u8_to_f32(u8_hwc.data_ptr(), B, H, W, Cc, out.data_ptr(), Fn._stream()),
+                   "dsmil_patches_u8_to_f32")
+    return out
+
+
+def format_bag_csv(feats: np.ndarray) -> str:
+    """The reference's wire format (compute_feats.py:80-82): pandas to_csv(index=False, float_format='%.4f')."""
+    feats = np.asarray(feats)
+    lines = [",".join(str(i) for i in range(feats.shape[1]))]
+    lines += [",".join("%.4f" % v for v in row) for row in feats]
+    return "\n".join(lines) + "\n"
+
+
+def write_bag_csv(feats: np.ndarray, save_path: str, bag_dir: str) -> str:
+    cls, name = bag_dir.split(os.path.sep)[-2], bag_dir.split(os.path.sep)[-1]
+    os.makedirs(os.path.join(save_path, cls), exist_ok=True)
+    out = os.path.join(save_path, cls, name + ".csv")
+    with open(out, "w") as f:
+        f.write(format_bag_csv(feats))
+    return out
+
+
+class _Staging:
+    """Two pinned uint8 batch buffers + their device twins; batch b+1 is decoded/copied while b is embedded."""
+
+    def __init__(self, batch: int, H: int, W: int, device):
+        self.host = [torch.empty(batch, H, W, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.dev = [torch.empty(batch, H, W, 3, dtype=torch.uint8, device=device) for _ in range(2)]
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.stream = torch.cuda.Stream(device=device)
+
+
+@torch.no_grad()
+def embed_bag(paths: Sequence[str], i_classifier, batch_size: int = 128, num_workers: int = 4,
+              device: Optional[torch.device] = None):
+    """Features [N, D] (device) and instance scores [N, C] (device) of one bag of patch files."""
+    dev = device or next(i_classifier.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("embed_bag needs the model on a CUDA device (no CPU path)")
+    if not paths:
+        return None, None
+    i_classifier.eval()
+    first = _decode_u8(paths[0])
+    H, W = first.shape[:2]
+    feats_out, cls_out = [], []
+    with torch.cuda.device(dev), ThreadPoolExecutor(max_workers=max(1, num_workers)) as pool:
+        st = _Staging(batch_size, H, W, dev)
+        compute = torch.cuda.current_stream()
+        for s in range(2):
+            st.consumed[s].record(compute)
+        batches = [paths[i:i + batch_size] for i in range(0, len(paths), batch_size)]
+        pending = None
+
+        def stage(bi):
+            s = bi % 2
+            imgs = list(pool.map(_decode_u8, batches[bi]))
+            st.consumed[s].synchronize()                    # the previous user of this slot has read it
+            hb = st.host[s]
+            for j, im in enumerate(imgs):
+                if im.shape != (H, W, 3):
+                    raise ValueError(f"patch {batches[bi][j]} is {im.shape}, expected {(H, W, 3)}")
+                hb[j].copy_(torch.from_numpy(im))
+            n = len(imgs)
+            with torch.cuda.stream(st.stream):
+                st.dev[s][:n].copy_(hb[:n], non_blocking=True)
+                st.copied[s].record(st.stream)
+            return s, n
+
+        pending = stage(0)
+        for bi in range(len(batches)):
+            s, n = pending
+            compute.wait_event(st.copied[s])
+            x = patches_to_float(st.dev[s][:n])
+            st.consumed[s].record(compute)
+            if bi + 1 < len(batches):
+                pending = stage(bi + 1)                     # overlaps with the backbone of this batch
+            feats, classes = i_classifier(x)
+            feats_out.append(feats)
+            cls_out.append(classes)
+    return torch.cat(feats_out), torch.cat(cls_out)
+
+
+def compute_feats(args, bags_list, i_classifier, save_path=None, magnification="single",
+                  sink: Optional[Callable[[str, torch.Tensor, torch.Tensor], None]] = None):
+    """Mirror of compute_feats.compute_feats (compute_feats.py:58-82).  `args` needs batch_size / num_workers.
+    save_path: write the reference CSV per bag (None: skip).  sink(bag_dir, feats_dev, classes_dev): optional
+    device-side hand-off (e.g. straight into the aggregator) that avoids the CSV round trip."""
+    num_bags = len(bags_list)
+    for i, bag_dir in enumerate(bags_list):
+        paths = list_patches(bag_dir, magnification)
+        feats, classes = embed_bag(paths, i_classifier, getattr(args, "batch_size", 128), getattr(args, "num_workers", 4))
+        sys.stdout.write("\r Computed: {}/{}".format(i + 1, num_bags))
+        if feats is None:
+            print("No valid patch extracted from: " + bag_dir)   # compute_feats.py:77-78
+            continue
+        if sink is not None:
+            sink(bag_dir, feats, classes)
+        if save_path is not None:
+            write_bag_csv(feats.cpu().numpy(), save_path, bag_dir)

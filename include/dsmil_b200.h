@@ -74,6 +74,10 @@ int dsmil_abi_version(void);
 const char* dsmil_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 uint64_t dsmil_launch_count(void);
+/* Patch pre-processing of the embedding loop (compute_feats.py:19-46,72: PIL image -> VF.to_tensor ->
+ * .float().cuda()): uint8 HWC patches [B,H,W,Cc] (device) -> float32 CHW [B,Cc,H,W] = value / 255. */
+int dsmil_patches_u8_to_f32(const uint8_t* in, int64_t B, int32_t H, int32_t W, int32_t Cc, float* out, void* stream);
+
 /* Live per-kernel timing for the roofline report (bench.py): when enabled, tagged launches are
  * bracketed by CUDA events on the launching stream.  dsmil_profile_read synchronises those events,
  * returns summed milliseconds and launch counts per tag (arrays of 8: 0 scores, 1 q-mlp, 2 attend,
