@@ -443,11 +443,8 @@ inline int launch_attend_b(const AttendArgs& a, int nrecs, cudaStream_t st) {
   const size_t smem = sizeof(float) * C * D;
   const int NJ = D <= 512 ? 1 : (D <= 1024 ? 2 : 4);
   auto go = [&](auto kern) -> int {
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
+    if (smem > 48 * 1024)
       DSMIL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      configured = smem;
-    }
     prof_begin(PROF_ATTEND, st);
     kern<<<nrecs, 256, smem, st>>>(a);
     prof_end(PROF_ATTEND, st);

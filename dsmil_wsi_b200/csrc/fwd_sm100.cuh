@@ -656,11 +656,9 @@ inline int launch_qmlp(const dsmil_params_t* p, const BagDev* bags_dev, int bag0
   const size_t smem = qmlp_smem_bytes(C, D);
   const int grid = ntiles < num_sms ? ntiles : num_sms;
   auto go = [&](auto kern) -> int {
-    static size_t configured = 0;   // per instantiation
-    if (configured < smem) {
-      DSMIL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      configured = smem;
-    }
+    // (set on every launch: the instantiations share one function-pointer TYPE, so a cached flag here would be
+    //  shared between them -- found by the D=1024 / C=1 shape tests; the call costs ~1 us of host time)
+    DSMIL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     prof_begin(PROF_FUSED, st);
     kern<<<grid, kThreads, smem, st>>>(a);
     prof_end(PROF_FUSED, st);

@@ -310,3 +310,49 @@ def test_forward_bags_generic_shapes_loop():
     for o, X in zip(outs, Xs):
         t = orc.forward(X, p)
         _check_forward(o, t.classes, t.prediction_bag, t.A, t.B, t.idx, p, None, "generic bags")
+
+
+@pytest.mark.parametrize("D,C,N,kind", [(128, 1, 300, "normal"), (512, 3, 1000, "uniform"), (512, 4, 257, "normal"),
+                                        (1024, 2, 640, "uniform"), (2048, 1, 300, "normal"), (2048, 2, 129, "uniform"),
+                                        (512, 2, 1, "normal"), (512, 1, 2, "uniform"), (640, 2, 200, "normal")])
+def test_tensor_core_path_shapes_vs_oracle(D, C, N, kind):
+    """Every (D % 128 == 0, C <= 4) configuration of the tcgen05 path, incl. classes padded to 4 (C = 3), the
+    widest feature size of the reference backbones (2048, ResNet-50/101), two-chunk D = 128 and one-row bags."""
+    import ctypes
+    from dsmil_wsi_b200 import _lib
+    from dsmil_wsi_b200.sharded import milnet_params
+    from dsmil_wsi_b200 import functional as Fn
+    p = orc.random_params(D, C, 1000 + D + C, scale=1.5)
+    X = orc.synthetic_bag(N, D, 2000 + N, kind)
+    net = build_net(p).eval()
+    assert _lib.load().dsmil_forward_path(Fn.ParamPack(*milnet_params(net)).ref, N) == 2
+    x = torch.from_numpy(X).cuda()
+    with torch.no_grad():
+        out = net(x)
+        idx = net.critical_instances(x)
+        bags = net.forward_bags([x, x[: max(1, N // 2)]])
+    t = orc.forward(X, p)
+    _check_forward(out, t.classes, t.prediction_bag, t.A, t.B, t.idx, p, idx, f"D{D}C{C}N{N}")
+    for u, v in zip(bags[0], out):
+        assert torch.equal(u, v)
+    t2 = orc.forward(X[: max(1, N // 2)], p)
+    _check_forward(bags[1], t2.classes, t2.prediction_bag, t2.A, t2.B, t2.idx, p, None, "second bag")
+
+
+def test_training_step_on_tensor_core_path_matches_oracle_grads():
+    """fwd (tcgen05, Q/H1 saved row-major) + bwd on D=512, C=2, N=3000 against the fp64 manual backward."""
+    p = orc.random_params(512, 2, 55, scale=1.0)
+    X = orc.synthetic_bag(3000, 512, 56, "normal")
+    y = np.array([0.0, 1.0], np.float32)
+    net = build_net(p).train()
+    classes, pred, A, B = net(torch.from_numpy(X).cuda())
+    loss = caller_loss(classes, pred, torch.from_numpy(y).cuda())
+    loss.backward()
+    t = orc.forward(X, p)
+    tl, d_cls, d_pred = orc.caller_loss_grads(t, y)
+    assert abs(loss.item() - tl) < 3e-6
+    tg = orc.backward(X, p, t, d_cls, d_pred)
+    named = dict(net.named_parameters())
+    for k, v in tg.items():
+        r = rel_to_max(_np(named[grad_name(k, True)].grad), v)
+        assert r < (1e-3 if k in ("W1", "b1", "W2", "b2") else 5e-5), (k, r)
