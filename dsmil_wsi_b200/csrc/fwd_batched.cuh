@@ -177,13 +177,13 @@ k_attend_b(const AttendArgs a) {
         for (int e = 0; e < 4; ++e) acc[k][j][e] *= scl[k];
     }
     const float* xb = bg.X + r0 * D;
-#pragma unroll 4
+#pragma unroll 8
     for (int r = half; r < rows; r += 2) {
       float4 x[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int col = c4 + 128 * j;
-        x[j] = col < D4 ? __ldg(reinterpret_cast<const float4*>(xb + static_cast<long long>(r) * D) + col)
+        x[j] = col < D4 ? ldg_stream(reinterpret_cast<const float4*>(xb + static_cast<long long>(r) * D) + col)
                         : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
