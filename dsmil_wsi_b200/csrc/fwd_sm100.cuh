@@ -27,7 +27,7 @@ constexpr int kTileM = 128;            // rows per tile == UMMA M
 constexpr int kChunkK = 64;            // k per smem operand chunk: 64 bf16 = 128 B = one swizzle row
 constexpr int kTileBytes = kTileM * kChunkK * 2;       // 16 KiB: one [128 x 64] bf16 operand tile
 constexpr int kChunkBytes = 2 * kTileBytes;            // hi tile + lo tile
-constexpr int kAStages = 2;
+constexpr int kAStages = 4;            // converters may run 4 chunks (128 KB) ahead of the tensor core
 constexpr int kWStages = 2;
 constexpr int kConvWarps = 16;           // 512 converter threads: 4 float4 per thread per 32 KB chunk
 constexpr int kEpiWarps = 8;             // two warps per TMEM lane quadrant, each takes 64 of the 128 columns
@@ -247,8 +247,7 @@ __device__ __forceinline__ float fast_tanh(float x) {
 }
 
 // dynamic smem carve (bytes, from a 1024-aligned base)
-constexpr int kOffW2 = 0;                                   // 2 chunks x 32 KiB
-constexpr int kOffWRing = kOffW2 + 2 * kChunkBytes;         // kWStages x 32 KiB
+constexpr int kOffWRing = 0;                                // kWStages x 32 KiB: W1 chunks AND the two W2 chunks stream here
 constexpr int kOffARing = kOffWRing + kWStages * kChunkBytes;
 constexpr int kOffWi = kOffARing + kAStages * kChunkBytes;  // C*D floats
 constexpr int kSmemFixed = kOffWi;
@@ -271,7 +270,7 @@ k_qmlp_sm100(const QmlpArgs a) {
   // barrier indices
   enum { A_FULL = 0, A_EMPTY = A_FULL + kAStages, W_FULL = A_EMPTY + kAStages, W_EMPTY = W_FULL + kWStages,
          H1_FULL = W_EMPTY + kWStages, H1_EMPTY = H1_FULL + 2, A2_FULL = H1_EMPTY + 2, A2_EMPTY, Q_FULL, Q_EMPTY,
-         W2_FULL, NBARS };
+         NBARS };
   static_assert(NBARS <= 32, "too many barriers");
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
 
@@ -286,7 +285,6 @@ k_qmlp_sm100(const QmlpArgs a) {
     for (int b = 0; b < 2; ++b) { mbar_init(bar(H1_FULL + b), 1); mbar_init(bar(H1_EMPTY + b), kEpiWarps * 32); }
     mbar_init(bar(A2_FULL), kEpiWarps * 32); mbar_init(bar(A2_EMPTY), 1);
     mbar_init(bar(Q_FULL), 1); mbar_init(bar(Q_EMPTY), kEpiWarps * 32);
-    mbar_init(bar(W2_FULL), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kWarpMma) {  // TMEM allocation (whole 512 columns; one CTA per SM by construction)
@@ -425,48 +423,52 @@ k_qmlp_sm100(const QmlpArgs a) {
     // =============================== W1 image producer (bulk copies) ==========================
     reg_dec<kRegsCtl>();
     if (lane == 0) {
-      mbar_expect_tx(bar(W2_FULL), 2 * kChunkBytes);
-      bulk_g2s(smem_u32(smem + kOffW2), a.w2img, 2 * kChunkBytes, bar(W2_FULL));
+      // chunk order == the MMA issuer's consumption order: tile it: W1 chunks 0..n-1, then the two W2 chunks of
+      // layer 2 of tile it-1; after the last tile its own two W2 chunks
       uint32_t stage = 0, phase = 0;
-      for (int tile = a.tile0 + blockIdx.x; tile < tile_end; tile += gridDim.x) {
-        for (int kc = 0; kc < nchunks; ++kc) {
-          mbar_wait(bar(W_EMPTY + stage), phase ^ 1, (a.mode & 64) ? 100 : 0);
-          if ((a.mode & 32) && tile != a.tile0 + static_cast<int>(blockIdx.x)) {   // experiment: no W streaming
-            mbar_arrive(bar(W_FULL + stage));
-          } else {
-          mbar_expect_tx(bar(W_FULL + stage), kChunkBytes);
-          bulk_g2s(smem_u32(smem + kOffWRing + stage * kChunkBytes), a.w1img + static_cast<size_t>(kc) * kChunkBytes,
-                   kChunkBytes, bar(W_FULL + stage));
-          }
-          if (++stage == kWStages) { stage = 0; phase ^= 1; }
-        }
+      auto push = [&](const uint8_t* src) {
+        mbar_wait(bar(W_EMPTY + stage), phase ^ 1);
+        mbar_expect_tx(bar(W_FULL + stage), kChunkBytes);
+        bulk_g2s(smem_u32(smem + kOffWRing + stage * kChunkBytes), src, kChunkBytes, bar(W_FULL + stage));
+        if (++stage == kWStages) { stage = 0; phase ^= 1; }
+      };
+      int it = 0;
+      for (int tile = a.tile0 + blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
+        for (int kc = 0; kc < nchunks; ++kc) push(a.w1img + static_cast<size_t>(kc) * kChunkBytes);
+        if (it > 0) { push(a.w2img); push(a.w2img + kChunkBytes); }
       }
+      if (it > 0) { push(a.w2img); push(a.w2img + kChunkBytes); }
     }
   } else if (warp == kWarpMma) {
     // =============================== MMA issuer ================================================
     reg_dec<kRegsCtl>();
     if (lane == 0) {
       uint32_t as = 0, aph = 0, ws = 0, wph = 0;
-      const uint32_t w2base = smem_u32(smem + kOffW2);
-      auto issue_l2 = [&](int j) {   // layer 2 of the j-th local tile: Qacc = A2(tmem) * W2^T
+      auto issue_l2 = [&](int j) {   // layer 2 of the j-th local tile: Qacc = A2(tmem) * W2^T, W2 from the W ring
         DSMIL_TRACE(1, 3, j);
         mbar_wait(bar(A2_FULL), j & 1);
         DSMIL_TRACE(1, 4, j);
         mbar_wait(bar(Q_EMPTY), (j & 1) ^ 1);
         DSMIL_TRACE(1, 5, j);
         tc_fence_after();
-#pragma unroll 2
-        for (int ks = 0; ks < ((a.mode & 8) ? 0 : 8); ++ks) {
-          const uint32_t bhi = desc_lo(w2base + (ks >> 2) * kChunkBytes + (ks & 3) * 32);
-          const uint32_t blo = bhi + (kTileBytes >> 4);
-          mma_ts2(tm_q, tm_a2hi + ks * 8, bhi, ks > 0);
-          mma_ts2(tm_q, tm_a2lo + ks * 8, bhi, 1);
-          mma_ts2(tm_q, tm_a2hi + ks * 8, blo, 1);
+#pragma unroll 1
+        for (int c2 = 0; c2 < 2; ++c2) {
+          mbar_wait(bar(W_FULL + ws), wph);
+          tc_fence_after();
+          const uint32_t wb = desc_lo(smem_u32(smem + kOffWRing + ws * kChunkBytes));
+#pragma unroll
+          for (int k4 = 0; k4 < ((a.mode & 8) ? 0 : 4); ++k4) {
+            const int ks = c2 * 4 + k4;
+            mma_ts2(tm_q, tm_a2hi + ks * 8, wb + k4 * 2, ks > 0);
+            mma_ts2(tm_q, tm_a2lo + ks * 8, wb + k4 * 2, 1);
+            mma_ts2(tm_q, tm_a2hi + ks * 8, wb + (kTileBytes >> 4) + k4 * 2, 1);
+          }
+          tc_commit(bar(W_EMPTY + ws));
+          if (++ws == kWStages) { ws = 0; wph ^= 1; }
         }
         tc_commit(bar(Q_FULL));
         tc_commit(bar(A2_EMPTY));
       };
-      mbar_wait(bar(W2_FULL), 0);
       int it = 0;
       for (int tile = a.tile0 + blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
         const int b = it & 1;
