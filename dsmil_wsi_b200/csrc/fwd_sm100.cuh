@@ -66,19 +66,19 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// try_wait with a suspend-time hint: the warp is parked by the hardware until the phase flips (or ~20 us pass)
-// instead of burning issue slots in a poll loop -- the spinning roles share schedulers with the converters.
+// Waiting roles share warp schedulers with the busy ones and the kernel is issue-bound, so a failed probe
+// backs off with nanosleep (sleep_ns > 0) instead of re-polling at full rate.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t sleep_ns = 0) {
-  (void)sleep_ns;
   uint32_t done = 0, spins = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) break;
-    if (++spins > (1u << 20)) __trap();  // ~20 s: a protocol bug must not hang the GPU
+    if (sleep_ns) __nanosleep(sleep_ns);
+    if (++spins > (1u << 26)) __trap();  // a protocol bug must not hang the GPU
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -252,7 +252,9 @@ constexpr int kOffARing = kOffWRing + kWStages * kChunkBytes;
 constexpr int kOffWi = kOffARing + kAStages * kChunkBytes;  // C*D floats
 constexpr int kSmemFixed = kOffWi;
 
-template <int CT>
+// CT: classes rounded up to 1/2/4/8.  DT: compile-time feature size (512 = every shipped configuration:
+// the chunk loops unroll and the load offsets become immediates) or 0 = run-time D.
+template <int CT, int DT>
 __global__ void __launch_bounds__(kThreads, 1)
 k_qmlp_sm100(const QmlpArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -263,8 +265,8 @@ k_qmlp_sm100(const QmlpArgs a) {
   __shared__ __align__(16) float s_b1[kQ], s_b2[kQ];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int D = a.D, C = a.C;
-  const int nchunks = D / kChunkK;
+  const int D = DT ? DT : a.D, C = a.C;
+  const int nchunks = DT ? DT / kChunkK : a.D / kChunkK;
   const int tile_end = a.tile0 + a.ntiles;
 
   // barrier indices
@@ -314,6 +316,7 @@ k_qmlp_sm100(const QmlpArgs a) {
     int tile = a.tile0 + blockIdx.x;
     // state of the tile whose chunks are being LOADED (may already be the next tile): 32-bit row numbers
     uint32_t ld_N = 0, ld_row = 0;               // rows in the bag, first row of the tile (+ r0)
+    bool ld_full = false;                        // whole 128-row tile inside the bag: unpredicated loads
     long long ld_rowoff = 0;
     const float4* xrow = nullptr;
     auto open_tile = [&](int t) {
@@ -322,13 +325,19 @@ k_qmlp_sm100(const QmlpArgs a) {
       ld_N = static_cast<uint32_t>(bp->N);
       ld_rowoff = bp->row_off;
       ld_row = static_cast<uint32_t>(t - bp->tile_off) * kTileM + r0;
+      ld_full = ld_row - r0 + kTileM <= ld_N;
       xrow = reinterpret_cast<const float4*>(bp->X + static_cast<long long>(ld_row) * D) + seg;
     };
     auto load_chunk = [&](int kc, float4* dst) {
+      if (ld_full) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4* src = xrow + static_cast<long long>(i) * (8ll * D) + kc * (kChunkK / 4);   // 32 rows apart
-        dst[i] = (ld_row + 32 * i < ld_N) ? ldg_stream(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i) dst[i] = ldg_stream(xrow + static_cast<long long>(i) * (8ll * D) + kc * (kChunkK / 4));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4* src = xrow + static_cast<long long>(i) * (8ll * D) + kc * (kChunkK / 4);   // 32 rows apart
+          dst[i] = (ld_row + 32 * i < ld_N) ? ldg_stream(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     };
     float4 cur[4], nxt[4];
@@ -341,7 +350,7 @@ k_qmlp_sm100(const QmlpArgs a) {
 #pragma unroll
         for (int k = 0; k < CT; ++k) wk[k] = lds128(swi_u32 + static_cast<uint32_t>(k * D + kc * kChunkK + seg * 4) * 4u);
       }
-      mbar_wait(bar(A_EMPTY + stage), phase ^ 1);
+      mbar_wait(bar(A_EMPTY + stage), phase ^ 1, 128);
       const uint32_t hi_tile = a_ring_u32 + stage * kChunkBytes + off0;   // shared-space addresses: STS with
       const uint32_t lo_tile = hi_tile + kTileBytes;                       // immediate offsets
 #pragma unroll
@@ -378,6 +387,7 @@ k_qmlp_sm100(const QmlpArgs a) {
         for (int k = 0; k < CT; ++k) sc[i][k] = 0.f;
       const int next_tile = tile + gridDim.x;
       // two chunks per iteration: the buffers swap roles, no register copies (nchunks is even: D % 128 == 0)
+#pragma unroll
       for (int kc = 0; kc < nchunks; kc += 2) {
         load_chunk(kc + 1, nxt);
         process(cur, kc);
@@ -427,7 +437,7 @@ k_qmlp_sm100(const QmlpArgs a) {
       // layer 2 of tile it-1; after the last tile its own two W2 chunks
       uint32_t stage = 0, phase = 0;
       auto push = [&](const uint8_t* src) {
-        mbar_wait(bar(W_EMPTY + stage), phase ^ 1);
+        mbar_wait(bar(W_EMPTY + stage), phase ^ 1, 256);
         mbar_expect_tx(bar(W_FULL + stage), kChunkBytes);
         bulk_g2s(smem_u32(smem + kOffWRing + stage * kChunkBytes), src, kChunkBytes, bar(W_FULL + stage));
         if (++stage == kWStages) { stage = 0; phase ^= 1; }
@@ -507,7 +517,7 @@ k_qmlp_sm100(const QmlpArgs a) {
     const int row_in_tile = (warp & 3) * 32 + lane;
     const int col0 = (warp >> 2) * 64;
     auto q_epilogue = [&](int j, long long grow, bool live, int qtile) {   // grow: packed row of this thread
-      mbar_wait(bar(Q_FULL), j & 1, (a.mode & 64) ? 200 : 0);
+      mbar_wait(bar(Q_FULL), j & 1, 256);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = col0; c0 < col0 + 64; c0 += 16) {
@@ -552,9 +562,9 @@ k_qmlp_sm100(const QmlpArgs a) {
       const bool live = n < bg.N;
       const long long grow = bg.row_off + n;
       const int b = it & 1;
-      mbar_wait(bar(H1_FULL + b), (it >> 1) & 1, (a.mode & 64) ? 200 : 0);
+      mbar_wait(bar(H1_FULL + b), (it >> 1) & 1, 512);
       if (tid == 0) DSMIL_TRACE(2, 0, it);
-      mbar_wait(bar(A2_EMPTY), (it & 1) ^ 1, (a.mode & 64) ? 200 : 0);     // layer 2 of the previous tile has consumed A2
+      mbar_wait(bar(A2_EMPTY), (it & 1) ^ 1, 128);     // layer 2 of the previous tile has consumed A2
       if (tid == 0) DSMIL_TRACE(2, 3, it);
       tc_fence_after();
 #pragma unroll 1
@@ -667,10 +677,16 @@ inline int launch_qmlp(const dsmil_params_t* p, const BagDev* bags_dev, int bag0
     DSMIL_LAUNCH_OK("k_qmlp_sm100");
     return 0;
   };
-  if (C == 1) return go(k_qmlp_sm100<1>);
-  if (C == 2) return go(k_qmlp_sm100<2>);
-  if (C <= 4) return go(k_qmlp_sm100<4>);
-  return go(k_qmlp_sm100<8>);
+  if (D == 512) {
+    if (C == 1) return go(k_qmlp_sm100<1, 512>);
+    if (C == 2) return go(k_qmlp_sm100<2, 512>);
+    if (C <= 4) return go(k_qmlp_sm100<4, 512>);
+    return go(k_qmlp_sm100<8, 512>);
+  }
+  if (C == 1) return go(k_qmlp_sm100<1, 0>);
+  if (C == 2) return go(k_qmlp_sm100<2, 0>);
+  if (C <= 4) return go(k_qmlp_sm100<4, 0>);
+  return go(k_qmlp_sm100<8, 0>);
 }
 
 }  // namespace sm100
