@@ -270,7 +270,7 @@ k_qmlp_sm100(const QmlpArgs a) {
   const int tile_end = a.tile0 + a.ntiles;
 
   // barrier indices
-  enum { A_FULL = 0, A_EMPTY = A_FULL + kAStages, W_FULL = A_EMPTY + kAStages, W_EMPTY = W_FULL + kWStages,
+  enum { A_FULL = 0, A_EMPTY = A_FULL + kAStages, A_WRITTEN = A_EMPTY + kAStages, W_FULL = A_WRITTEN + kAStages, W_EMPTY = W_FULL + kWStages,
          H1_FULL = W_EMPTY + kWStages, H1_EMPTY = H1_FULL + 2, A2_FULL = H1_EMPTY + 2, A2_EMPTY, Q_FULL, Q_EMPTY,
          NBARS };
   static_assert(NBARS <= 32, "too many barriers");
@@ -282,7 +282,9 @@ k_qmlp_sm100(const QmlpArgs a) {
     for (int i = tid; i < CT * D; i += kThreads) sWi[i] = (i < C * D) ? a.Wi[i] : 0.f;
   if (tid < kQ) { s_b1[tid] = a.b1[tid]; s_b2[tid] = a.b2[tid]; }
   if (tid == 0) {
-    for (int s = 0; s < kAStages; ++s) { mbar_init(bar(A_FULL + s), kConvWarps); mbar_init(bar(A_EMPTY + s), 1); }
+    for (int s = 0; s < kAStages; ++s) {
+      mbar_init(bar(A_WRITTEN + s), kConvWarps); mbar_init(bar(A_FULL + s), 1); mbar_init(bar(A_EMPTY + s), 1);
+    }
     for (int s = 0; s < kWStages; ++s) { mbar_init(bar(W_FULL + s), 1); mbar_init(bar(W_EMPTY + s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar(H1_FULL + b), 1); mbar_init(bar(H1_EMPTY + b), kEpiWarps * 32); }
     mbar_init(bar(A2_FULL), kEpiWarps * 32); mbar_init(bar(A2_EMPTY), 1);
@@ -372,9 +374,11 @@ k_qmlp_sm100(const QmlpArgs a) {
         sts64(hi_tile + i * 4096, u01, u23);
         sts64(lo_tile + i * 4096, *reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
       }
-      fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (required: tested)
+      // No proxy fence here: fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the MEMBAR would
+      // wait for this thread's prefetched global loads (a full HBM latency per chunk).  The stores are released to
+      // the fence warp (mbarrier arrive = release), which has no loads in flight, fences, and publishes A_FULL.
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(A_FULL + stage));
+      if (lane == 0) mbar_arrive(bar(A_WRITTEN + stage));
       if (++stage == kAStages) { stage = 0; phase ^= 1; }
     };
     while (tile < tile_end) {
@@ -427,8 +431,22 @@ k_qmlp_sm100(const QmlpArgs a) {
       }
       tile = next_tile;
     }
+  } else if (warp == kWarpTma + 1) {
+    // ====== proxy-fence warp: generic-proxy A tiles -> async proxy, then hand the stage to the MMA issuer ======
+    reg_dec<kRegsCtl>();
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = a.tile0 + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+        for (int kc = 0; kc < nchunks; ++kc) {
+          mbar_wait(bar(A_WRITTEN + stage), phase);
+          fence_proxy_async();
+          mbar_arrive(bar(A_FULL + stage));
+          if (++stage == kAStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
   } else if (warp >= kWarpMma && warp != kWarpMma && warp != kWarpTma) {
-    reg_dec<kRegsCtl>();     // idle warps of the control warpgroup
+    reg_dec<kRegsCtl>();     // idle warp of the control warpgroup
   } else if (warp == kWarpTma) {
     // =============================== W1 image producer (bulk copies) ==========================
     reg_dec<kRegsCtl>();
