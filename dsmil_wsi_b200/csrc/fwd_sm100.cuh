@@ -203,6 +203,8 @@ inline int debug_mode() {
   return m;
 }
 
+constexpr int kSmemBags = 96;
+
 struct QmlpArgs {
   const BagDev* bags;
   int bag0, nb;           // bags [bag0, bag0+nb) are covered by this launch ...
@@ -263,6 +265,7 @@ k_qmlp_sm100(const QmlpArgs a) {
   __shared__ __align__(8) uint64_t bars[32];
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) float s_b1[kQ], s_b2[kQ];
+  __shared__ BagDev s_bags[kSmemBags];           // the launch's slice of the bag table (tile-boundary lookups)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = DT ? DT : a.D, C = a.C;
@@ -281,6 +284,11 @@ k_qmlp_sm100(const QmlpArgs a) {
   if (do_scores)
     for (int i = tid; i < CT * D; i += kThreads) sWi[i] = (i < C * D) ? a.Wi[i] : 0.f;
   if (tid < kQ) { s_b1[tid] = a.b1[tid]; s_b2[tid] = a.b2[tid]; }
+  const bool tbl_in_smem = a.nb <= kSmemBags;
+  if (tbl_in_smem)
+    for (int i = tid; i < a.nb; i += kThreads) s_bags[i] = a.bags[a.bag0 + i];
+  // cursors below index the table relative to bag0 when it is cached in shared memory
+  const BagDev* tbl = tbl_in_smem ? s_bags : a.bags + a.bag0;
   if (tid == 0) {
     for (int s = 0; s < kAStages; ++s) {
       mbar_init(bar(A_WRITTEN + s), kConvWarps); mbar_init(bar(A_FULL + s), 1); mbar_init(bar(A_EMPTY + s), 1);
@@ -312,7 +320,7 @@ k_qmlp_sm100(const QmlpArgs a) {
     const uint32_t off0 = swz_off(r0, seg * 4);  // rows r0 + 32 i share (row & 7): offset_i = off0 + 4096 i
     const uint32_t a_ring_u32 = smem_u32(smem + kOffARing), swi_u32 = smem_u32(smem + kOffWi);
     uint32_t stage = 0, phase = 0;
-    TileCursor cur_bag(a.bags, a.bag0, a.nb);
+    TileCursor cur_bag(tbl, 0, a.nb);
     // The loop is flat over (tile, k-chunk): `nxt` always holds the NEXT chunk -- of this tile or the first
     // chunk of the CTA's next tile -- so the HBM stream never drains at a tile boundary.
     int tile = a.tile0 + blockIdx.x;
@@ -323,7 +331,7 @@ k_qmlp_sm100(const QmlpArgs a) {
     const float4* xrow = nullptr;
     auto open_tile = [&](int t) {
       cur_bag.seek(t);
-      const BagDev* bp = a.bags + cur_bag.bag;
+      const BagDev* bp = tbl + cur_bag.bag;
       ld_N = static_cast<uint32_t>(bp->N);
       ld_rowoff = bp->row_off;
       ld_row = static_cast<uint32_t>(t - bp->tile_off) * kTileM + r0;
@@ -382,7 +390,7 @@ k_qmlp_sm100(const QmlpArgs a) {
       if (++stage == kAStages) { stage = 0; phase ^= 1; }
     };
     while (tile < tile_end) {
-      const int my_bag = cur_bag.bag;            // this tile's bag (the load state may move on below)
+      const int my_bag = a.bag0 + cur_bag.bag;   // this tile's bag (the load state may move on below)
       const uint32_t t_N = ld_N, t_row = ld_row;
       const long long t_rowoff = ld_rowoff;
 #pragma unroll
@@ -572,10 +580,10 @@ k_qmlp_sm100(const QmlpArgs a) {
     int it = 0, prev_tile = 0;
     long long prev_grow = 0;
     bool prev_live = false;
-    TileCursor cur_bag(a.bags, a.bag0, a.nb);
+    TileCursor cur_bag(tbl, 0, a.nb);
     for (int tile = a.tile0 + blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
       cur_bag.seek(tile);
-      const BagDev bg = a.bags[cur_bag.bag];
+      const BagDev bg = tbl[cur_bag.bag];
       const long long n = static_cast<long long>(tile - bg.tile_off) * kTileM + row_in_tile;
       const bool live = n < bg.N;
       const long long grow = bg.row_off + n;
