@@ -242,6 +242,42 @@ struct TileCursor {
   }
 };
 
+// Packed fp32x2 arithmetic (sm_100: add/mul/fma.f32x2 issue one instruction for two lanes' values) -- the
+// epilogue is issue-bound, so halving its FADD/FMUL/FFMA count matters.  Results are bit-identical to scalar ops.
+struct f2 { float x, y; };
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+// two tanh at once: 1 - 2/(exp2(x * 2log2e) + 1); same formula and intrinsics as fast_tanh
+__device__ __forceinline__ f2 fast_tanh2(f2 x) {
+  const f2 t = mul2(x, f2{2.8853900817779268f, 2.8853900817779268f});
+  f2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(t.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(t.y));
+  const f2 d = add2(e, f2{1.f, 1.f});
+  f2 r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
+  return fma2(r, f2{-2.f, -2.f}, f2{1.f, 1.f});
+}
 __device__ __forceinline__ float fast_tanh(float x) {
   // tanh(x) = 1 - 2/(exp(2x)+1); ex2.approx + rcp.approx: |err| < ~3e-7 absolute, saturates correctly
   const float e = __expf(2.f * x);
@@ -557,10 +593,12 @@ k_qmlp_sm100(const QmlpArgs a) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 bb = *reinterpret_cast<const float4*>(&s_b2[c0 + 4 * q]);
-            dst[(4 * q + 0) * kTileM] = fast_tanh(__uint_as_float(v[4 * q + 0]) + bb.x);
-            dst[(4 * q + 1) * kTileM] = fast_tanh(__uint_as_float(v[4 * q + 1]) + bb.y);
-            dst[(4 * q + 2) * kTileM] = fast_tanh(__uint_as_float(v[4 * q + 2]) + bb.z);
-            dst[(4 * q + 3) * kTileM] = fast_tanh(__uint_as_float(v[4 * q + 3]) + bb.w);
+            const f2 t0 = fast_tanh2(add2(f2{__uint_as_float(v[4 * q + 0]), __uint_as_float(v[4 * q + 1])}, f2{bb.x, bb.y}));
+            const f2 t1 = fast_tanh2(add2(f2{__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])}, f2{bb.z, bb.w}));
+            dst[(4 * q + 0) * kTileM] = t0.x;
+            dst[(4 * q + 1) * kTileM] = t0.y;
+            dst[(4 * q + 2) * kTileM] = t1.x;
+            dst[(4 * q + 3) * kTileM] = t1.y;
           }
         } else if (live && !(a.mode & 16)) {
           float4* dst = reinterpret_cast<float4*>((a.mode & 1) ? a.Q + (threadIdx.x & 255) * 4 : a.Q + grow * kQ + c0);
@@ -606,13 +644,15 @@ k_qmlp_sm100(const QmlpArgs a) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float2 bb = *reinterpret_cast<const float2*>(&s_b1[c0 + 2 * q]);
-          const float h0 = fmaxf(__uint_as_float(v[2 * q]) + bb.x, 0.f);
-          const float h1 = fmaxf(__uint_as_float(v[2 * q + 1]) + bb.y, 0.f);
+          const f2 z = add2(f2{__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])}, f2{bb.x, bb.y});
+          const float h0 = fmaxf(z.x, 0.f), h1 = fmaxf(z.y, 0.f);
           v[2 * q] = __float_as_uint(h0);
           v[2 * q + 1] = __float_as_uint(h1);
           const __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1);
-          const __nv_bfloat162 ll = __floats2bfloat162_rn(h0 - __low2float(hh), h1 - __high2float(hh));
-          hi[q] = *reinterpret_cast<const uint32_t*>(&hh);
+          const uint32_t hu = *reinterpret_cast<const uint32_t*>(&hh);
+          const f2 res = add2(f2{h0, h1}, f2{-__uint_as_float(hu << 16), -__uint_as_float(hu & 0xffff0000u)});
+          const __nv_bfloat162 ll = __floats2bfloat162_rn(res.x, res.y);
+          hi[q] = hu;
           lo[q] = *reinterpret_cast<const uint32_t*>(&ll);
         }
         DSMIL_TMEM_ST8(tm_a2hi + lane_sel + (c0 >> 1), hi);
