@@ -5,6 +5,7 @@ aggregator runs in libdsmil_b200.so.  CPU tensors are rejected: there is no CPU 
 """
 from __future__ import annotations
 
+import collections.abc
 import ctypes as C
 from typing import Optional, Sequence, Tuple
 
@@ -218,6 +219,35 @@ def mil_forward(feats, params: Sequence[Optional[torch.Tensor]], v_input=None, v
     return MILForwardFn.apply(want_grad, feats, v_input, v_mask, classes_in, *params)
 
 
+class BagOutputs(collections.abc.Sequence):
+    """Per-bag (classes, prediction_bag, A, B) views over the packed outputs of dsmil_forward_bags, created on
+    access: materialising 4 views per bag eagerly costs ~1.5 us each on the host -- as long as the GPU work of a
+    16-bag step -- so the sequence hands them out lazily.  `.packed` exposes the packed tensors themselves."""
+
+    def __init__(self, classes, pred, A, B, Ns):
+        self.packed = (classes, pred, A, B)
+        self.Ns = list(Ns)
+        self._offsets = None
+
+    def __len__(self):
+        return len(self.Ns)
+
+    def __getitem__(self, b):
+        if isinstance(b, slice):
+            return [self[i] for i in range(*b.indices(len(self)))]
+        if b < 0:
+            b += len(self)
+        if not 0 <= b < len(self):
+            raise IndexError(b)
+        if self._offsets is None:
+            self._offsets = [0]
+            for n in self.Ns:
+                self._offsets.append(self._offsets[-1] + n)
+        lo, hi = self._offsets[b], self._offsets[b + 1]
+        classes, pred, A, B = self.packed
+        return classes[lo:hi], pred[b:b + 1], A[lo:hi], B[b:b + 1]
+
+
 @torch.no_grad()
 def mil_forward_bags(bags: Sequence[torch.Tensor], params: Sequence[Optional[torch.Tensor]]):
     """Inference forward of a STREAM of bags in one library call (dsmil_forward_bags): returns a list of
@@ -249,8 +279,4 @@ def mil_forward_bags(bags: Sequence[torch.Tensor], params: Sequence[Optional[tor
         rc = lib.dsmil_forward_bags(P.ref, c_X, c_N, nb, _ptr(classes), _ptr(pred), _ptr(A), _ptr(B), _ptr(crit),
                                     _ptr(ws), ws.numel(), _stream())
         _lib.check(rc, "dsmil_forward_bags")
-    outs, row = [], 0
-    for b, n in enumerate(Ns):
-        outs.append((classes[row:row + n], pred[b:b + 1], A[row:row + n], B[b:b + 1]))
-        row += n
-    return outs, crit
+    return BagOutputs(classes, pred, A, B, Ns), crit

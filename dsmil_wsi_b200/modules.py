@@ -132,8 +132,9 @@ class MILNet(nn.Module):
 
     @torch.no_grad()
     def forward_bags(self, bags):
-        """Throughput form: a list of bags [N_i, D] -> list of (classes, prediction_bag, A, B), computed by ONE
-        library call (bag table, L2-sized sub-batches).  Inference only (no autograd)."""
+        """Throughput form: a list of bags [N_i, D] -> sequence of (classes, prediction_bag, A, B), computed by ONE
+        library call (bag table).  The result is a lazy sequence of views over packed outputs
+        (`.packed`).  Inference only (no autograd)."""
         ic, bc = self.i_classifier, self.b_classifier
         if not (isinstance(bc, BClassifier) and isinstance(ic, (FCLayer, IClassifier))):
             return [self.forward(b) for b in bags]
