@@ -33,6 +33,7 @@ SIGNATURES = {
     "dsmil_abi_version": (C.c_int, []),
     "dsmil_last_error": (C.c_char_p, []),
     "dsmil_launch_count": (C.c_uint64, []),
+    "dsmil_gather_rows": (C.c_int, [C.c_void_p, c_i64, C.c_int32, C.c_void_p, c_i64, C.c_void_p, C.c_void_p]),
     "dsmil_patches_u8_to_f32": (C.c_int, [C.c_void_p, c_i64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "dsmil_profile_enable": (C.c_int, [C.c_int]),
     "dsmil_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

@@ -36,6 +36,27 @@ void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::m
 
 namespace sm100 { long long* g_trace_buf = nullptr; }
 
+// train_tcga.py:78-83 dropout_patches: `feats[random_indices]` -- a row gather.  One warp per output row.
+__global__ void __launch_bounds__(256)
+k_gather_rows(const float* __restrict__ X, int D, const long long* __restrict__ idx, long long M,
+              float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long stride = static_cast<long long>(gridDim.x) * 8;
+  const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  for (long long m = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5); m < M; m += stride) {
+    const float* src = X + idx[m] * D;
+    float* dst = out + m * D;
+    if (vec) {
+      for (int j = lane; j < (D >> 2); j += 32)
+        reinterpret_cast<float4*>(dst)[j] = __ldg(reinterpret_cast<const float4*>(src) + j);
+    } else {
+      for (int j = lane; j < D; j += 32) dst[j] = __ldg(src + j);
+    }
+  }
+}
+
+
+
 // compute_feats.py:19-46 (PIL -> VF.to_tensor): uint8 HWC -> float32 CHW, value / 255 (an IEEE division, as
 // torchvision's `img.div(255)`), done on the device so that patches cross PCIe as bytes (4x less H2D traffic).
 __global__ void __launch_bounds__(256)
@@ -475,6 +496,15 @@ int dsmil_forward_path(const dsmil_params_t* p, int64_t N) {
 /* Debug: CTA-0 timeline of the tensor-core kernel (clock64 stamps).  buf = device int64[3*8*64] or NULL. */
 int dsmil_debug_set_trace(void* buf) {
   sm100::g_trace_buf = static_cast<long long*>(buf);
+  return 0;
+}
+
+int dsmil_gather_rows(const float* X, int64_t N, int32_t D, const int64_t* idx, int64_t M, float* out, void* stream) {
+  DSMIL_REQUIRE(N >= 0 && M >= 0 && D >= 1 && (M == 0 || (X && idx && out)), "bad arguments");
+  if (M == 0) return 0;
+  const int grid = static_cast<int>(std::min<int64_t>((M + 7) / 8, 148 * 8));
+  k_gather_rows<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(X, D, reinterpret_cast<const long long*>(idx), M, out);
+  DSMIL_LAUNCH_OK("k_gather_rows");
   return 0;
 }
 

@@ -74,6 +74,10 @@ int dsmil_abi_version(void);
 const char* dsmil_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 uint64_t dsmil_launch_count(void);
+/* Caller-side bag feed: `feats[random_indices]` of dropout_patches (train_tcga.py:78-83) as a
+ * device row gather: out[m,:] = X[idx[m],:], idx int64 on the device, rows in [0,N). */
+int dsmil_gather_rows(const float* X, int64_t N, int32_t D, const int64_t* idx, int64_t M, float* out, void* stream);
+
 /* Patch pre-processing of the embedding loop (compute_feats.py:19-46,72: PIL image -> VF.to_tensor ->
  * .float().cuda()): uint8 HWC patches [B,H,W,Cc] (device) -> float32 CHW [B,Cc,H,W] = value / 255. */
 int dsmil_patches_u8_to_f32(const uint8_t* in, int64_t B, int32_t H, int32_t W, int32_t Cc, float* out, void* stream);
