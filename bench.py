@@ -96,7 +96,7 @@ class ClockSampler:
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm),
-                "window": "warm-up (>= 0.6 s of identical steps) + timed region, nvidia-smi -lms 100"}
+                "window": "warm-up (0.6 s of identical steps at N=1, 512 steps under torchrun) + timed region, nvidia-smi -lms 100"}
 
 
 class Weights:
@@ -248,17 +248,27 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # clocks / throttle reasons are sampled from the warm-up on (the timed region alone lasts a few ms, shorter
-    # than nvidia-smi's fastest period), i.e. across >= 0.6 s of the same steps under load + the timed region
+    # than nvidia-smi's fastest period).  The number of warm-up steps MUST be identical on every rank (each
+    # step contains collectives), so it is a fixed count under torchrun and time-based only for a single process.
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    t_w = time.perf_counter()
-    n_w = 0
-    while n_w < max(args.warmup, 3) or time.perf_counter() - t_w < 0.6:
+    for _ in range(max(args.warmup, 3)):
         step()
-        n_w += 1
-        if n_w % 8 == 0:
-            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    if world == 1:
+        t_w = time.perf_counter()
+        n_w = 0
+        while time.perf_counter() - t_w < 0.6:
+            step()
+            n_w += 1
+            if n_w % 8 == 0:
+                torch.cuda.synchronize()
+    else:
+        for n_w in range(1, 513):          # same count on all ranks
+            step()
+            if n_w % 8 == 0:
+                torch.cuda.synchronize()
     barrier()
     l0 = lib.dsmil_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
