@@ -211,7 +211,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a collective that cannot complete (e.g. a rank died) aborts after 3 minutes instead of hanging the box
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     from dsmil_wsi_b200 import _lib
     from dsmil_wsi_b200.pipeline import HostBagPipeline
     from dsmil_wsi_b200.sharded import (CudaShardBagOps, CudaShardOps, milnet_params, sharded_forward_bags,
