@@ -49,6 +49,14 @@ def load_peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
+def warmup_plan(world: int, warmup: int):
+    """(fixed_steps, timed_seconds, extra_fixed_steps).  Under torchrun every step contains collectives, so the
+    number of warm-up steps must be the same on all ranks: fixed counts only.  A single process may extend the
+    warm-up by wall-clock time so that the clock sampler sees >= 0.6 s of load."""
+    fixed = max(int(warmup), 3)
+    return (fixed, 0.6, 0) if world == 1 else (fixed, 0.0, 512)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -255,22 +263,21 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    fixed_steps, timed_s, extra_steps = warmup_plan(world, args.warmup)
+    for _ in range(fixed_steps):
         step()
     torch.cuda.synchronize()
-    if world == 1:
-        t_w = time.perf_counter()
-        n_w = 0
-        while time.perf_counter() - t_w < 0.6:
-            step()
-            n_w += 1
-            if n_w % 8 == 0:
-                torch.cuda.synchronize()
-    else:
-        for n_w in range(1, 513):          # same count on all ranks
-            step()
-            if n_w % 8 == 0:
-                torch.cuda.synchronize()
+    t_w = time.perf_counter()
+    n_w = 0
+    while time.perf_counter() - t_w < timed_s:        # single process only (timed_s == 0 under torchrun)
+        step()
+        n_w += 1
+        if n_w % 8 == 0:
+            torch.cuda.synchronize()
+    for n_w in range(1, extra_steps + 1):              # same count on all ranks
+        step()
+        if n_w % 8 == 0:
+            torch.cuda.synchronize()
     barrier()
     l0 = lib.dsmil_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
