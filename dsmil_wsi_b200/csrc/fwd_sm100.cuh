@@ -1,18 +1,24 @@
-// sm_100a tensor-core path of phase 1 (dsmil.py:11 scores + :49 Q-MLP), D % 64 == 0.
+// sm_100a tensor-core path of phase 1 (dsmil.py:11 scores + :49 Q-MLP), D % 128 == 0.
 //
-//   k_prep_wimg     packs W1 / W2 into bf16 hi/lo "images" that are byte-for-byte the shared-memory
+//   k_prep_wimg2    packs W1 / W2 into bf16 hi/lo "images" that are byte-for-byte the shared-memory
 //                   operand tiles tcgen05.mma reads (K-major, SWIZZLE_128B), so they can be brought
 //                   in with plain 1-D bulk copies (cp.async.bulk -> SASS UBLKCP), no tensor map.
-//   k_qmlp_sm100    persistent, warp-specialised, one CTA per SM, 128-row tiles:
-//        converter warps : coalesced float4 loads of X from HBM -> fp32 FFMA instance scores (+ arg-max
-//                          key) -> split x = hi + lo (two bf16) -> swizzled st.shared operand tiles
-//        TMA warp        : streams the W1 image chunk by chunk (L2-resident) into a smem ring
-//        MMA warp        : one thread issues tcgen05.mma (M=128,N=128,K=16, bf16 in, fp32 accumulate in
+//   k_qmlp_sm100    persistent, warp-specialised, one CTA per SM, 128-row tiles walked through a bag table
+//                   (ragged batch of bags), 896 threads in warpgroup-aligned roles (setmaxnreg 80/72/40):
+//        converters x16  : streaming 16-byte loads of X (one 32 KB chunk ahead, across tile boundaries) ->
+//                          fp32 FFMA instance scores (+ packed arg-max key per bag) -> x = hi + lo (two bf16)
+//                          -> swizzled st.shared operand tiles; release to the fence warp (no MEMBAR here)
+//        fence warp      : fence.proxy.async per stage, then publishes A_FULL to the MMA issuer
+//        W producer      : streams the W1 chunks and, per tile, the two W2 chunks into a 2-stage smem ring
+//        MMA issuer      : one thread issues tcgen05.mma (M=128,N=128,K=16, bf16 in, fp32 accumulate in
 //                          TMEM); 3 products per K-step: hi*Whi + lo*Whi + hi*Wlo  ("3xBF16", error at
-//                          the fp32 noise floor -- SURVEY A.4, tests/test_oracle.py)
-//        epilogue warps  : H1 = relu(acc + b1) -> bf16 hi/lo written BACK to TMEM (tcgen05.st) as the A
-//                          operand of layer 2 (A-from-TMEM MMA); Q = tanh(acc2 + b2) -> global
+//                          the fp32 noise floor -- SURVEY A.4, tests/test_oracle.py); layer 2: A from TMEM
+//        epilogue x8     : H1 = relu(acc + b1) -> bf16 hi/lo written BACK to TMEM (tcgen05.st) as the A
+//                          operand of layer 2; Q = tanh(acc2 + b2) (packed f32x2 math) -> global, in tile
+//                          blocks (column-major, coalesced) or row-major when training keeps it
+//   smem (196 KB): W ring 2 x 32 KB | A ring 4 x 32 KB (hi tile + lo tile) | Wi rows
 //   TMEM columns (512): H1 accumulators 2 x 128 | Q accumulator 128 | A2 hi 64 | A2 lo 64
+//   Measured state and what limits it: DESIGN.md section 4.1, profiles/.
 #pragma once
 #include <cuda_bf16.h>
 #include <type_traits>
