@@ -97,36 +97,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]
-__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]
-__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-#define DSMIL_TMEM_LD32(taddr, v)                                                                          \
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                   \
-               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                                   \
-               "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                  \
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),       \
-                 "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),   \
-                 "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),\
-                 "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),\
-                 "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                        \
-               : "r"(taddr) : "memory")
-#define DSMIL_TMEM_ST16(taddr, v)                                                                          \
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                             \
-               "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                                 \
-               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),  \
-                 "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]),          \
-                 "r"(v[14]), "r"(v[15]) : "memory")
 #define DSMIL_TMEM_LD16(taddr, v)                                                                          \
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                   \
                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                            \
@@ -144,10 +114,6 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) = 1024 B between
 // 8-row groups | version [46,48) = 1 (sm_100) | layout [61,64) = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return static_cast<uint64_t>((saddr & 0x3ffffu) >> 4) | (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
-         (1ull << 46) | (2ull << 61);
-}
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 // The same descriptor as two 32-bit words: only the low word (start address) changes between MMAs.
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -176,20 +142,7 @@ __host__ __device__ inline uint32_t swz_off(int row, int k) {
 
 // ---- weight images -----------------------------------------------------------------------
 // img layout: for each 64-wide k chunk: [hi tile 16 KiB][lo tile 16 KiB], rows = output features (128)
-__global__ void __launch_bounds__(256)
-k_prep_wimg(const float* __restrict__ W, int K, uint8_t* __restrict__ img) {
-  const int total = 128 * K;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int n = i / K, k = i % K;
-    const float w = W[i];
-    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-    uint8_t* chunk = img + static_cast<size_t>(k / kChunkK) * kChunkBytes;
-    const uint32_t off = swz_off(n, k % kChunkK);
-    *reinterpret_cast<__nv_bfloat16*>(chunk + off) = hi;
-    *reinterpret_cast<__nv_bfloat16*>(chunk + kTileBytes + off) = lo;
-  }
-}
+// (written by k_prep_wimg2 below, once per parameter version)
 
 // One bag of a batch, as the kernels see it (device memory, built by the host per call).
 struct BagDev {
