@@ -139,11 +139,24 @@ def embed_bag(paths: Sequence[str], i_classifier, batch_size: int = 128, num_wor
     return torch.cat(feats_out), torch.cat(cls_out)
 
 
+def write_bag_container(feats: np.ndarray, save_path: str, bag_dir: str) -> str:
+    """Same naming as write_bag_csv, `.bin` container (formats.write_bag_bin): exact fp32, 4 B/value."""
+    from .formats import write_bag_bin
+    cls, name = bag_dir.split(os.path.sep)[-2], bag_dir.split(os.path.sep)[-1]
+    os.makedirs(os.path.join(save_path, cls), exist_ok=True)
+    out = os.path.join(save_path, cls, name + ".bin")
+    write_bag_bin(out, feats)
+    return out
+
+
 def compute_feats(args, bags_list, i_classifier, save_path=None, magnification="single",
-                  sink: Optional[Callable[[str, torch.Tensor, torch.Tensor], None]] = None):
+                  sink: Optional[Callable[[str, torch.Tensor, torch.Tensor], None]] = None, wire: str = "csv"):
     """Mirror of compute_feats.compute_feats (compute_feats.py:58-82).  `args` needs batch_size / num_workers.
-    save_path: write the reference CSV per bag (None: skip).  sink(bag_dir, feats_dev, classes_dev): optional
-    device-side hand-off (e.g. straight into the aggregator) that avoids the CSV round trip."""
+    save_path: write one file per bag (None: skip) -- wire="csv" is the reference's `%.4f` text, "bin" the
+    binary container, "both" writes the two.  sink(bag_dir, feats_dev, classes_dev): optional device-side
+    hand-off (e.g. straight into the aggregator) that avoids any file round trip."""
+    if wire not in ("csv", "bin", "both"):
+        raise ValueError(f"wire must be 'csv', 'bin' or 'both', got {wire!r}")
     num_bags = len(bags_list)
     for i, bag_dir in enumerate(bags_list):
         paths = list_patches(bag_dir, magnification)
@@ -155,4 +168,8 @@ def compute_feats(args, bags_list, i_classifier, save_path=None, magnification="
         if sink is not None:
             sink(bag_dir, feats, classes)
         if save_path is not None:
-            write_bag_csv(feats.cpu().numpy(), save_path, bag_dir)
+            host = feats.cpu().numpy()
+            if wire in ("csv", "both"):
+                write_bag_csv(host, save_path, bag_dir)
+            if wire in ("bin", "both"):
+                write_bag_container(host, save_path, bag_dir)

@@ -56,6 +56,32 @@ class DeviceBagStore:
         for p in paths:
             self.add_stacked(torch.load(p, map_location="cpu"))
 
+    def add_bag(self, feats: torch.Tensor, label: torch.Tensor) -> None:
+        """feats [N, D] and label [C] given separately (no stacked copy)."""
+        if feats.dim() != 2 or feats.shape[1] != self.D:
+            raise ValueError(f"feats must be [N, {self.D}], got {tuple(feats.shape)}")
+        self.bags.append((feats.to(self.device, dtype=torch.float32, non_blocking=True).contiguous(),
+                          label.to(self.device, dtype=torch.float32).reshape(1, -1)))
+
+    def add_bins(self, paths: Iterable[str]) -> None:
+        """Binary bag containers (formats.write_bag_bin): payload read straight into pinned memory, then one
+        asynchronous H2D copy per bag -- no text parse, no [N, D + C] intermediate."""
+        from . import formats
+        pin = self.device.type == "cuda"
+        for p in paths:
+            feats, label = formats.read_bag_bin(p, pin_memory=pin)
+            self.add_bag(feats, label)
+        if pin:
+            torch.cuda.current_stream(self.device).synchronize()   # pinned sources may be freed after this
+
+    def add_index(self, index_csv: str, num_classes: int, tcga_default: bool = False) -> None:
+        """The reference's route (train_tcga.py:245-250 + :36-51) without the temp_train/*.pt detour."""
+        from . import formats
+        for entry, label in formats.read_dataset_index(index_csv):
+            csv = formats.tcga_default_feats_path(entry) if tcga_default else entry
+            self.add_bag(torch.from_numpy(formats.read_bag_csv(csv)),
+                         torch.from_numpy(formats.bag_label(label, num_classes)))
+
     def __len__(self):
         return len(self.bags)
 
