@@ -37,7 +37,20 @@ def list_patches(bag_dir: str, magnification: str = "single") -> List[str]:
     if magnification == "high":
         return (glob.glob(os.path.join(bag_dir, "*" + os.sep + "*.jpg")) +
                 glob.glob(os.path.join(bag_dir, "*" + os.sep + "*.jpeg")))
-    raise ValueError(f"magnification {magnification!r} not handled here (tree mode is a later row, SURVEY 8f-4)")
+    raise ValueError(f"magnification {magnification!r} is not a single-level listing; tree mode has its own "
+                     "traversal (list_tree_patches / compute_tree_feats)")
+
+
+def list_tree_patches(bag_dir: str):
+    """Two-magnification traversal of compute_feats.py:91,100-103: the low-magnification patches of the bag
+    folder (jpg then jpeg) and, per low patch `<x>.jp(e)g`, the high-magnification patches in folder `<x>/`.
+    Returns (low_paths, [high_paths of low 0, high_paths of low 1, ...])."""
+    low = glob.glob(os.path.join(bag_dir, "*.jpg")) + glob.glob(os.path.join(bag_dir, "*.jpeg"))
+    high = []
+    for lp in low:
+        folder = os.path.dirname(lp) + os.sep + os.path.splitext(os.path.basename(lp))[0]
+        high.append(glob.glob(folder + os.sep + "*.jpg") + glob.glob(folder + os.sep + "*.jpeg"))
+    return low, high
 
 
 def _decode_u8(path: str) -> np.ndarray:
@@ -137,6 +150,65 @@ def embed_bag(paths: Sequence[str], i_classifier, batch_size: int = 128, num_wor
             feats_out.append(feats)
             cls_out.append(classes)
     return torch.cat(feats_out), torch.cat(cls_out)
+
+
+def fuse_tree_feats(high: torch.Tensor, low: torch.Tensor, parent: torch.Tensor, mode: str) -> torch.Tensor:
+    """Row m of the tree bag from high-magnification row m and its parent low-magnification row
+    (compute_feats.py:111-116): 'fusion' -> high + 0.25 * low[parent] ([M, D]); 'cat' -> [high | low[parent]]
+    ([M, 2D]).  Works on whatever device the operands live on; fp32 results equal the reference's numpy
+    expression bit for bit (0.25 * x is exact, one rounding in the add)."""
+    if mode not in ("fusion", "cat"):
+        raise NotImplementedError(f"{mode} is not an excepted option for --tree_fusion. This argument accepts 2 "
+                                  "options: 'fusion' and 'cat'.")          # wording of compute_feats.py:116
+    if high.dim() != 2 or low.dim() != 2 or high.shape[1] != low.shape[1]:
+        raise ValueError(f"high {tuple(high.shape)} and low {tuple(low.shape)} must be [M, D] and [L, D]")
+    if parent.numel() != high.shape[0]:
+        raise ValueError("one parent index per high-magnification row")
+    par = low.index_select(0, parent.to(device=low.device, dtype=torch.int64))
+    if mode == "fusion":
+        return high + 0.25 * par
+    return torch.cat((high, par), dim=-1)
+
+
+def compute_tree_feats(args, bags_list, embedder_low, embedder_high, save_path=None,
+                       sink: Optional[Callable[[str, torch.Tensor], None]] = None, wire: str = "csv", embed=None):
+    """Mirror of compute_feats.compute_tree_feats (compute_feats.py:84-126); `args` needs batch_size,
+    num_workers, tree_fusion.
+
+    The reference embeds every high-magnification patch as its own batch of one (one PIL open, one H2D, ~60
+    launches and one D2H per patch) and fuses in numpy on the host.  Here all high patches of a bag go through
+    the same double-buffered uint8 staging loop as the low ones (`embed_bag`, full batches -- InstanceNorm is
+    per-sample, so batch composition does not change a patch's features), the parent gather + fusion is one
+    device op, and the bag leaves the device once.  Row order is the reference's: low patches in listing
+    order, within each its high patches in listing order; low patches without a folder contribute nothing.
+    `embed(paths, embedder, batch_size, num_workers) -> (feats, classes)` defaults to `embed_bag`."""
+    if wire not in ("csv", "bin", "both"):
+        raise ValueError(f"wire must be 'csv', 'bin' or 'both', got {wire!r}")
+    mode = getattr(args, "tree_fusion", "cat")
+    if mode not in ("fusion", "cat"):
+        fuse_tree_feats(torch.empty(0, 1), torch.empty(0, 1), torch.empty(0, dtype=torch.int64), mode)   # raises
+    embed = embed or embed_bag
+    bs, nw = getattr(args, "batch_size", 128), getattr(args, "num_workers", 4)
+    num_bags = len(bags_list)
+    for i, bag_dir in enumerate(bags_list):
+        low_paths, high_lists = list_tree_patches(bag_dir)
+        high_paths = [p for hl in high_lists for p in hl]
+        sys.stdout.write("\r Computed: {}/{} -- {}/{}".format(i + 1, num_bags, len(low_paths), len(low_paths)))
+        if not high_paths:
+            print("No valid patch extracted from: " + bag_dir)   # compute_feats.py:120-121
+            continue
+        low_feats, _ = embed(low_paths, embedder_low, bs, nw)
+        high_feats, _ = embed(high_paths, embedder_high, bs, nw)
+        parent = torch.tensor([j for j, hl in enumerate(high_lists) for _ in hl], dtype=torch.int64)
+        feats = fuse_tree_feats(high_feats, low_feats, parent, mode)
+        if sink is not None:
+            sink(bag_dir, feats)
+        if save_path is not None:
+            host = feats.cpu().numpy()
+            if wire in ("csv", "both"):
+                write_bag_csv(host, save_path, bag_dir)
+            if wire in ("bin", "both"):
+                write_bag_container(host, save_path, bag_dir)
 
 
 def write_bag_container(feats: np.ndarray, save_path: str, bag_dir: str) -> str:
