@@ -88,3 +88,25 @@ def test_split_precision_emulation_is_at_fp32_floor():
     e1 = rel_to_max(orc.bf16_round(X).astype(np.float64) @ orc.bf16_round(p.W1).astype(np.float64).T, truth)
     f32 = rel_to_max((X @ p.W1.T).astype(np.float64), truth)
     assert e3 < 6e-6 and e1 > 50 * e3, (e3, e1, f32)
+
+
+@pytest.mark.parametrize("name", ["shipped_tcga", "shipped_c16", "rand_d512_c2", "rand_d512_c1"])
+def test_apriori_softmax_bound_on_tanh_path(name):
+    """with a tanh-bounded Q, |L| <= ||q_max||_1 / sqrt(128f), so exp(L - bound) needs no running
+    max; A and B from plain sums stay at the oracle's fp32 noise floor."""
+    from conftest import load_golden, rel_to_max
+    g, p, X = load_golden(name)
+    X = X.astype(np.float32)
+    Q = orc.q_mlp(X, p)[0].astype(np.float32)
+    idx = orc.critical_instances(X @ p.Wi.T + p.bi)
+    qmax = Q[idx]
+    s = np.float32(np.sqrt(np.float32(128)))
+    L = (Q @ qmax.T) / s
+    bound = (np.abs(qmax).sum(1) / s).astype(np.float32)
+    assert (np.abs(L) <= bound[None, :] * (1 + 1e-6)).all() and bound.max() <= 11.3138
+    e = np.exp((L - bound[None, :]).astype(np.float32))
+    assert e.min() > 1e-10                                   # far from denormals: e^-22.7 = 1.4e-10 is the floor
+    S = e.sum(0, dtype=np.float64)
+    A = (e / S).astype(np.float32)
+    B = (e.astype(np.float64).T @ X.astype(np.float64)) / S[:, None]
+    assert rel_to_max(A, g["A"]) < 5e-6 and rel_to_max(B, g["B"].reshape(B.shape)) < 5e-6
