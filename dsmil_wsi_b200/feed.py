@@ -104,3 +104,81 @@ def train_epoch(milnet, store: DeviceBagStore, criterion, optimizer, dropout_pat
         optimizer.step()
         total += loss.detach()
     return float(total.item()) / max(1, len(order))
+
+
+def eval_epoch(milnet, store: DeviceBagStore, criterion, average: bool = False, bags_per_launch: int = 16,
+               dropout_patch: float = 0.0, generator: Optional[torch.Generator] = None):
+    """The measuring half of train_tcga.test() (train_tcga.py:85-107): mean loss, labels [n_bags, C] and
+    sigmoid predictions [n_bags, C] (`average=True`: sigmoid(max) + sigmoid(bag), as `args.average`).  The ROC /
+    threshold logic that follows in the reference (:108-132) is the caller's and works on these arrays.
+
+    Bags go through `milnet.forward_bags` `bags_per_launch` at a time when the module has it (one batched launch
+    sequence for the whole group, the slides/sec path), else one `milnet(x)` per bag; the loss terms stay on the
+    device and there is one host sync per epoch instead of two `.item()` per bag.  The reference also routes test
+    bags through `dropout_patches` (a row permutation when dropout_patch == 0); a permutation does not change
+    any output of the operator except the order of the per-instance rows, so it is skipped unless rows are
+    actually dropped."""
+    milnet.eval()
+    n = len(store)
+    if n == 0:
+        raise ValueError("eval_epoch over an empty store")
+    losses, labels, preds = [], [], []
+    batched = hasattr(milnet, "forward_bags") and bags_per_launch > 1
+    with torch.no_grad():
+        for s in range(0, n, max(1, bags_per_launch)):
+            group = store.bags[s:s + max(1, bags_per_launch)]
+            xs = [dropout_patches(f, 1 - dropout_patch, generator) if dropout_patch > 0 else f for f, _ in group]
+            outs = milnet.forward_bags(xs) if batched else [milnet(x) for x in xs]
+            for (ins_prediction, bag_prediction, _, _), (_, label) in zip(outs, group):
+                max_prediction, _ = torch.max(ins_prediction, 0)
+                losses.append(0.5 * criterion(bag_prediction.view(1, -1), label.view(1, -1)) +
+                              0.5 * criterion(max_prediction.view(1, -1), label.view(1, -1)))
+                labels.append(label.view(-1))
+                p = torch.sigmoid(bag_prediction).view(-1)
+                preds.append(torch.sigmoid(max_prediction).view(-1) + p if average else p)
+    loss = float(torch.stack([l.reshape(()) for l in losses]).mean().item())
+    return loss, torch.stack(labels).cpu().numpy().astype(int), torch.stack(preds).cpu().numpy()
+
+
+# ---- classic-MIL drivers (train_mil.py) ---------------------------------------------------------------------
+
+
+def mil_store(bags: Sequence[Tuple[int, "np.ndarray"]], device="cuda") -> DeviceBagStore:
+    """`formats.mil_bags(...)` output -> device-resident store (label as a [1, 1] target, train_mil.py:49)."""
+    if not bags:
+        raise ValueError("no bags")
+    store = DeviceBagStore(int(bags[0][1].shape[1]), device=device)
+    for label, x in bags:
+        store.add_bag(torch.as_tensor(x, dtype=torch.float32), torch.tensor([float(label)]))
+    return store
+
+
+def cross_validation_set(in_list: Sequence, fold: int, index: int):
+    """train_mil.py:99-104: chunks of int(len/fold) items; chunk `index` is the test set, the rest (including
+    the short tail chunk the integer division leaves) the training set."""
+    items = list(in_list)
+    n = int(len(items) / fold)
+    if n < 1:
+        raise ValueError(f"{len(items)} bags cannot be split into {fold} folds")
+    chunks = [items[i:i + n] for i in range(0, len(items), n)]
+    test = chunks.pop(index)
+    return [x for c in chunks for x in c], test
+
+
+def compute_pos_weight(bags: Sequence[Tuple[int, object]]) -> float:
+    """train_mil.py:106-110: negatives / positives over the bag labels (clipped to {0, 1})."""
+    pos = sum(int(min(max(b[0], 0), 1)) for b in bags)
+    if pos == 0:
+        raise ZeroDivisionError("no positive bag in the training split (the reference divides by zero here too)")
+    return (len(bags) - pos) / pos
+
+
+def mil_epoch_train(milnet, store: DeviceBagStore, criterion, optimizer, order: Optional[Sequence[int]] = None) -> float:
+    """train_mil.epoch_train (train_mil.py:42-59): per bag, shuffle the instances, forward, 0.5/0.5 loss, step."""
+    return train_epoch(milnet, store, criterion, optimizer, dropout_patch=0.0, order=order)
+
+
+def mil_epoch_test(milnet, store: DeviceBagStore, criterion, bags_per_launch: int = 16):
+    """train_mil.epoch_test (train_mil.py:61-80): (mean loss, bag labels, sigmoid bag predictions)."""
+    loss, labels, preds = eval_epoch(milnet, store, criterion, average=False, bags_per_launch=bags_per_launch)
+    return loss, [int(l[0]) for l in labels], [p.squeeze() for p in preds]

@@ -104,6 +104,15 @@ def main():
             bag = train_mil.get_bag(data, b)
             gold[f"svm_bag{b}_label"] = np.int64(bag[0, 2])
             gold[f"svm_bag{b}_n"] = np.int64(bag.shape[0])
+        # fold bookkeeping of train_mil.py:99-110
+        for n_items, fold in ((23, 5), (92, 10), (10, 10)):
+            for index in range(fold):
+                tr, te = train_mil.cross_validation_set(list(range(n_items)), fold, index)
+                gold[f"cv_{n_items}_{fold}_{index}_train"] = np.array(tr, dtype=np.int64)
+                gold[f"cv_{n_items}_{fold}_{index}_test"] = np.array(te, dtype=np.int64)
+        labs = [-1, 1, 1, -1, -1, 0, 1, -1]
+        gold["pos_weight_labels"] = np.array(labs, dtype=np.int64)
+        gold["pos_weight"] = np.float64(train_mil.compute_pos_weight([[l, None] for l in labs]))
     finally:
         os.chdir(cwd)
     np.savez_compressed(os.path.join(OUT, "expected.npz"), **gold)
