@@ -794,6 +794,104 @@ int dsmil_backward(const dsmil_params_t* p, const float* X, const float* x_for_v
   return 0;
 }
 
+// ---- row-sharded backward: dsmil_backward cut at its two cross-row sums (+ the caller's grad all-reduce) ----
+static int shard_bwd_ws(const dsmil_params_t* p, int64_t N, void* ws, size_t cap, BwdWs* w) {
+  bool ok;
+  *w = carve_bwd(p, N, 0, ws, cap, &ok);
+  if (!ws || !ok) {
+    set_error("workspace too small: need %zu bytes, got %zu", w->bytes, cap);
+    return DSMIL_ERR_WORKSPACE;
+  }
+  return 0;
+}
+
+int dsmil_shard_backward_phase1(const dsmil_params_t* p, const float* X, int64_t N, const float* A, const float* B,
+                                const float* d_classes, const float* d_pred, float* dA, float* t_local, float* gWi,
+                                float* gbi, float* gWf, float* gbf, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  DSMIL_REQUIRE(!p->passing_v, "sharded backward supports the identity v only");
+  DSMIL_REQUIRE(N >= 0 && B && t_local && (N == 0 || (X && A && dA)), "NULL tensor pointer or N < 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = p->C, D = p->D;
+  BwdWs w;
+  if ((rc = shard_bwd_ws(p, N, workspace, workspace_bytes, &w))) return rc;
+  k_bwd_bag<<<ceil_div(static_cast<int64_t>(C) * D, 256), 256, 0, st>>>(p->Wf, B, d_pred, nullptr, C, D, w.dB, gWf, gbf);
+  DSMIL_LAUNCH_OK("k_bwd_bag");
+  if (gWi) {
+    if (d_classes && N > 0) { if ((rc = launch_gemm_tn(d_classes, C, X, D, N, w.tnpart, gWi, st))) return rc; }
+    else DSMIL_CUDA_OK(cudaMemsetAsync(gWi, 0, sizeof(float) * C * D, st));
+  }
+  if (gbi) {
+    if (d_classes && N > 0) { if ((rc = launch_colsum(d_classes, C, N, w.cspart, gbi, st))) return rc; }
+    else DSMIL_CUDA_OK(cudaMemsetAsync(gbi, 0, sizeof(float) * C, st));
+  }
+  if (N == 0) {
+    DSMIL_CUDA_OK(cudaMemsetAsync(t_local, 0, sizeof(float) * C, st));
+    return 0;
+  }
+  const size_t smem = sizeof(float) * C * D;
+  if (smem > 48 * 1024)
+    DSMIL_CUDA_OK(cudaFuncSetAttribute(k_rowdot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = static_cast<int>(std::min<int64_t>(ceil_div(N, 8), 148 * 8));
+  k_rowdot<<<grid, 256, smem, st>>>(X, N, D, w.dB, C, nullptr, dA);
+  DSMIL_LAUNCH_OK("k_rowdot");
+  const int gs = static_cast<int>(std::min<int64_t>(ceil_div(N, 256), 296));
+  k_bwd_t_partial<<<gs, 256, 0, st>>>(A, dA, N, C, w.tpart);
+  DSMIL_LAUNCH_OK("k_bwd_t_partial");
+  k_sum_partials<<<1, 256, 0, st>>>(w.tpart, gs, C, t_local);
+  DSMIL_LAUNCH_OK("k_sum_partials");
+  return 0;
+}
+
+int dsmil_shard_backward_phase2(const dsmil_params_t* p, int64_t N, const float* A, float* dA, const float* t_global,
+                                const float* Q, float* dqm_local, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  DSMIL_REQUIRE(N >= 0 && t_global && dqm_local && (N == 0 || (A && dA && Q)), "NULL tensor pointer or N < 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = p->C;
+  BwdWs w;
+  if ((rc = shard_bwd_ws(p, N, workspace, workspace_bytes, &w))) return rc;
+  if (N > 0) {
+    const int gs = static_cast<int>(std::min<int64_t>(ceil_div(N, 256), 296));
+    k_bwd_dL<<<gs, 256, 0, st>>>(A, dA, N, C, t_global, 1);
+    DSMIL_LAUNCH_OK("k_bwd_dL");
+  }
+  return launch_gemm_tn(dA, C, Q, kQ, N, w.tnpart, dqm_local, st);   // zeros when N == 0
+}
+
+int dsmil_shard_backward_phase3(const dsmil_params_t* p, const float* X, int64_t N, int64_t row_offset, const float* Q,
+                                const float* H1, const float* dL, const float* dqm_global, const float* q_max,
+                                const int64_t* crit_idx, float* gW1, float* gb1, float* gW2, float* gb2,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  DSMIL_REQUIRE(N >= 0 && dqm_global && q_max && crit_idx && (N == 0 || (X && Q && dL)), "NULL tensor pointer or N < 0");
+  DSMIL_REQUIRE(!p->nonlinear || N == 0 || H1, "nonlinear q backward needs saved H1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = p->D, C = p->C;
+  BwdWs w;
+  if ((rc = shard_bwd_ws(p, N, workspace, workspace_bytes, &w))) return rc;
+  const float* dz1 = w.dz2;
+  if (N > 0) {
+    const int grid = static_cast<int>(std::min<int64_t>(ceil_div(N * kQ, 256), 148 * 8));
+    k_bwd_dq_shard<<<grid, 256, 0, st>>>(dL, Q, q_max, dqm_global, crit_idx, N, row_offset, C, p->nonlinear, w.dz2);
+    DSMIL_LAUNCH_OK("k_bwd_dq_shard");
+  }
+  if (p->nonlinear) {
+    if (gW2 && (rc = launch_gemm_tn(w.dz2, kQ, H1, kQ, N, w.tnpart, gW2, st))) return rc;
+    if (gb2 && (rc = launch_colsum(w.dz2, kQ, N, w.cspart, gb2, st))) return rc;
+    if (N > 0 && (rc = launch_linear<ACT_MASK_POS, true>(w.dz2, N, kQ, p->W2, nullptr, kQ, w.dz1, H1, 0, st))) return rc;
+    dz1 = w.dz1;
+  }
+  if (gW1 && (rc = launch_gemm_tn(dz1, kQ, X, D, N, w.tnpart, gW1, st))) return rc;
+  if (gb1 && (rc = launch_colsum(dz1, kQ, N, w.cspart, gb1, st))) return rc;
+  return 0;
+}
+
 int dsmil_instance_scores_backward(const dsmil_params_t* p, const float* X, int64_t N, const float* d_classes,
                                    float* gWi, float* gbi, float* gX, void* workspace, size_t workspace_bytes,
                                    void* stream) {

@@ -130,6 +130,39 @@ k_bwd_dq(const float* __restrict__ dL, const float* __restrict__ Q, const float*
   }
 }
 
+// Row-sharded form of k_bwd_dq: q_max comes from the forward's exchange (the critical row may live on another
+// rank) and the dqm share is added where the GLOBAL row number n + row_offset equals crit[k].
+__global__ void __launch_bounds__(256)
+k_bwd_dq_shard(const float* __restrict__ dL, const float* __restrict__ Q, const float* __restrict__ qmax,
+               const float* __restrict__ dqm, const int64_t* __restrict__ crit, int64_t N, int64_t row_offset, int C,
+               int through_tanh, float* __restrict__ dz) {
+  __shared__ float sq[kMaxC][kQ];
+  __shared__ float sd[kMaxC][kQ];
+  __shared__ int64_t sidx[kMaxC];
+  for (int i = threadIdx.x; i < C * kQ; i += blockDim.x) {
+    sq[i / kQ][i % kQ] = qmax[i];
+    sd[i / kQ][i % kQ] = dqm[i];
+  }
+  if (threadIdx.x < C) sidx[threadIdx.x] = crit[threadIdx.x] - row_offset;
+  __syncthreads();
+  const int64_t total = N * kQ;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t n = i / kQ;
+    const int j = static_cast<int>(i % kQ);
+    float g = 0.f;
+    for (int k = 0; k < C; ++k) {
+      g = fmaf(dL[n * C + k], sq[k][j], g);
+      if (n == sidx[k]) g += sd[k][j];
+    }
+    if (through_tanh) {
+      const float q = Q[i];
+      g *= (1.f - q * q);
+    }
+    dz[i] = g;
+  }
+}
+
 // gX[n,d] (+)= sum_k dcls[n,k]*Wi[k,d] + sum_k A[n,k]*dB[k,d]   (either term optional)
 __global__ void __launch_bounds__(256)
 k_bwd_dx_extra(const float* __restrict__ dcls, const float* __restrict__ Wi, const float* __restrict__ A,

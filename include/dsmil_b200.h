@@ -171,6 +171,33 @@ int dsmil_shard_merge_partials(int32_t C, int32_t Dv, const float* recs, int32_t
 int dsmil_shard_phase3(const dsmil_params_t* p, int64_t N_local, const float* rec_global,
                        float* A, float* B, float* pred, void* stream);
 
+/* ---- row-sharded backward (SURVEY §8e "Backward", Appendix A.2 "Sharded"; identity v only) -----------
+ * Reverse pass of the sharded forward for the callers' loss (train_tcga.py:67-72): each rank keeps its rows of
+ * X, Q, H1 (saved by dsmil_shard_phase1), the normalised A of phase3 and the replicated B, q_max, crit_idx.
+ * Three reductions, done by the caller with NCCL all-reduce(sum) between the phases:
+ *   phase1: replicated gWf/gbf (not reduced), local partial gWi/gbi, dA_local[N,C], t_local[C] = sum_n A.dA
+ *           -> all-reduce t (C floats)
+ *   phase2: dA_local becomes dL_local in place (softmax-over-instances backward with the global t),
+ *           dqm_local[C,128] = dL^T Q  -> all-reduce dqm (C*128 floats)
+ *   phase3: MLP backward over the local rows; the critical rows' share dqm is added on the rank that owns
+ *           row crit_idx[k] (global index - row_offset); local partial gW1/gb1(/gW2/gb2)
+ *           -> all-reduce of the parameter gradients
+ * d_classes_local may be NULL (no gradient through the instance scores).  N_local may be 0 (all outputs
+ * zero).  Workspace: dsmil_backward_workspace_bytes(p, N_local, 0).  dsmil_backward == these three calls with
+ * one rank. */
+int dsmil_shard_backward_phase1(const dsmil_params_t* p, const float* X, int64_t N_local, const float* A,
+                                const float* B, const float* d_classes_local, const float* d_pred,
+                                float* dA_local, float* t_local, float* gWi, float* gbi, float* gWf, float* gbf,
+                                void* workspace, size_t workspace_bytes, void* stream);
+int dsmil_shard_backward_phase2(const dsmil_params_t* p, int64_t N_local, const float* A, float* dA_to_dL,
+                                const float* t_global, const float* Q, float* dqm_local,
+                                void* workspace, size_t workspace_bytes, void* stream);
+int dsmil_shard_backward_phase3(const dsmil_params_t* p, const float* X, int64_t N_local, int64_t row_offset,
+                                const float* Q, const float* H1, const float* dL_local, const float* dqm_global,
+                                const float* q_max, const int64_t* crit_idx,
+                                float* gW1, float* gb1, float* gW2, float* gb2,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
 /* The same three phases for a BATCH of row-sharded bags (tensor-core path; dsmil_shard_bags_supported):
  * every rank passes its local rows of all nb bags; records are packed per bag so that a whole step costs
  * two all-gathers.  Xs/Ns/row_offsets are host arrays; the workspace must be the same buffer in all three

@@ -346,6 +346,60 @@ def forward_sharded(X: np.ndarray, p: Params, G: int, dtype=np.float64) -> FwdOu
     return FwdOut(c_all, pred.reshape(1, C), A, Bm.reshape(1, C, Dv), gidx)
 
 
+def backward_sharded(X: np.ndarray, p: Params, out: FwdOut, d_classes: Optional[np.ndarray],
+                     d_pred: Optional[np.ndarray], G: int) -> Dict[str, np.ndarray]:
+    """Row-sharded reverse pass (SURVEY A.2 "Sharded", §8e): rank r holds rows [lo_r, hi_r) of X, classes, Q,
+    H1, A and the replicated B / q_max / critical indices from the sharded forward.  Three reductions:
+        reduce 1: t[k] = sum_n A[n,k] dA[n,k]                 (C scalars; the softmax-over-instances backward)
+        reduce 2: dq_max[k,:] = sum_n dL[n,k] Q[n,:]          (C x 128; applied on the critical row's owner)
+        reduce 3: parameter gradients                         (sum over ranks; Wf/bf are replicated, not summed)
+    Must reproduce ``backward`` (identity v only; tests assert it)."""
+    if p.passing_v:
+        raise NotImplementedError("sharded backward: identity v only")
+    f = np.float64
+    X = np.asarray(X, f)
+    p = p.astype(f)
+    C = p.C
+    A, Q, H1 = np.asarray(out.A, f), np.asarray(out.Q, f), (np.asarray(out.H1, f) if out.H1 is not None else None)
+    Bm = np.asarray(out.B, f).reshape(C, -1)
+    idx = out.idx
+    q_max = Q[idx]                                            # replicated by the forward's exchange 1
+    bounds = shard_bounds(X.shape[0], G)
+    dp = np.zeros(C) if d_pred is None else np.asarray(d_pred, f).reshape(C)
+    dc = np.zeros((X.shape[0], C)) if d_classes is None else np.asarray(d_classes, f)
+    # replicated on every rank: bag classifier and dB
+    g: Dict[str, np.ndarray] = {"Wf": np.outer(dp, Bm.reshape(-1)).reshape(C, C, -1), "bf": dp.copy()}
+    dB = (p.Wf.reshape(C, -1).T @ dp).reshape(C, -1)
+    # local part 1 + reduce 1
+    dA = [X[lo:hi] @ dB.T for lo, hi in bounds]
+    t = sum((A[lo:hi] * dA_r).sum(0) for (lo, hi), dA_r in zip(bounds, dA))
+    # local part 2 + reduce 2
+    dL = [A[lo:hi] * (dA_r - t) / f(SCALE_F32) for (lo, hi), dA_r in zip(bounds, dA)]
+    dqm = sum(dL_r.T @ Q[lo:hi] for (lo, hi), dL_r in zip(bounds, dL))
+    # local part 3 + reduce 3
+    names = ["Wi", "bi", "W1", "b1"] + (["W2", "b2"] if p.nonlinear else [])
+    for n in names:
+        g[n] = np.zeros_like(getattr(p, n))
+    for (lo, hi), dL_r in zip(bounds, dL):
+        Xr, Qr = X[lo:hi], Q[lo:hi]
+        dQ = dL_r @ q_max
+        for k in range(C):
+            if lo <= idx[k] < hi:                             # the owner of critical row k adds dq_max[k]
+                dQ[idx[k] - lo] += dqm[k]
+        if p.nonlinear:
+            dz2 = dQ * (1 - Qr * Qr)
+            g["W2"] += dz2.T @ H1[lo:hi]
+            g["b2"] += dz2.sum(0)
+            dz1 = (dz2 @ p.W2) * (H1[lo:hi] > 0)
+        else:
+            dz1 = dQ
+        g["W1"] += dz1.T @ Xr
+        g["b1"] += dz1.sum(0)
+        g["Wi"] += dc[lo:hi].T @ Xr
+        g["bi"] += dc[lo:hi].sum(0)
+    return g
+
+
 # --------------------------------------------------------------------------- split-precision emulation
 def bf16_round(a: np.ndarray) -> np.ndarray:
     """Round-to-nearest-even fp32 -> bf16 -> fp32 (finite inputs)."""

@@ -110,3 +110,19 @@ def test_apriori_softmax_bound_on_tanh_path(name):
     A = (e / S).astype(np.float32)
     B = (e.astype(np.float64).T @ X.astype(np.float64)) / S[:, None]
     assert rel_to_max(A, g["A"]) < 5e-6 and rel_to_max(B, g["B"].reshape(B.shape)) < 5e-6
+
+
+@pytest.mark.parametrize("name", ["shipped_tcga", "rand_d512_c1", "musk_d166_n7", "lin_d512_c3"])
+@pytest.mark.parametrize("G", [1, 2, 3, 8])
+def test_sharded_backward_algebra_reproduces_single_device(name, G):
+    """SURVEY A.2 "Sharded": three reductions (t, dq_max, parameter grads) give the single-device gradients."""
+    from conftest import load_golden, rel_to_max
+    g, p, X = load_golden(name)
+    out = orc.forward(X, p)
+    y = np.asarray(g["y"], np.float64).reshape(-1)
+    _, d_cls, d_pred = orc.caller_loss_grads(out, y)
+    one = orc.backward(X, p, out, d_cls, d_pred)
+    many = orc.backward_sharded(X, p, out, d_cls, d_pred, G)
+    assert set(many) == {k for k in one if k != "X"}
+    for k in many:
+        assert rel_to_max(many[k], one[k]) < 1e-12, k

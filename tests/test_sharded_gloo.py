@@ -33,7 +33,8 @@ class OracleShardOps:
         if N == 0:
             idx[:] = np.iinfo(np.int64).max
             cand[2 * C:3 * C] = -np.inf
-            return torch.zeros(0, C), torch.zeros(0, 128, dtype=torch.float64), X.double(), torch.from_numpy(cand)
+            return (torch.zeros(0, C, dtype=torch.float64), torch.zeros(0, 128, dtype=torch.float64), X.double(),
+                    torch.from_numpy(cand))
         c = x @ p.Wi.T + p.bi
         Q, _ = orc.q_mlp(x, p)
         li = orc.critical_instances(c)
@@ -147,3 +148,123 @@ def test_shard_bounds_cover_and_balance():
         sizes = [hi - lo for lo, hi in b]
         assert max(sizes) - min(sizes) <= 1
     assert shard_bounds(10, 3) == list(orc.shard_bounds(10, 3))
+
+
+# ---- sharded training step: forward + the three-reduction backward through autograd, over gloo -----------------
+
+
+class OracleTrainOps(OracleShardOps):
+    """+ the training phase 1 and the three backward phases, numpy fp64 with fp32 parameter gradients."""
+
+    def phase1_train(self, X, row_offset):
+        classes, Q, x, cand = self.phase1(X, row_offset)
+        H1 = None
+        if self.p.nonlinear:
+            H1 = torch.from_numpy(orc.q_mlp(x.numpy(), self.p)[1]) if x.shape[0] else torch.zeros(0, 128, dtype=torch.float64)
+        return classes, Q, H1, x, cand
+
+    def bwd1(self, X, A, B, d_classes, d_pred):
+        p, C, D = self.p, self.C, self.D
+        x, a = X.numpy().astype(np.float64), A.numpy().astype(np.float64)
+        dp = np.zeros(C) if d_pred is None else d_pred.numpy().astype(np.float64).reshape(C)
+        dc = np.zeros((x.shape[0], C)) if d_classes is None else d_classes.numpy().astype(np.float64)
+        Bm = B.numpy().astype(np.float64).reshape(C, D)
+        dB = (p.Wf.reshape(C, -1).T @ dp).reshape(C, D)
+        dA = x @ dB.T
+        f32 = lambda v: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
+        return (torch.from_numpy(dA), torch.from_numpy((a * dA).sum(0)), f32(dc.T @ x), f32(dc.sum(0)),
+                f32(np.outer(dp, Bm.reshape(-1)).reshape(C, C, D)), f32(dp))
+
+    def bwd2(self, A, dA, t, Q):
+        dL = A.numpy() * (dA.numpy() - t.numpy()) / np.float64(orc.SCALE_F32)
+        return torch.from_numpy(dL), torch.from_numpy(dL.T @ Q.numpy())
+
+    def bwd3(self, X, row_offset, Q, H1, dL, dqm, qmax, crit):
+        p, C = self.p, self.C
+        x, q = X.numpy().astype(np.float64), Q.numpy()
+        dQ = dL.numpy() @ qmax.numpy().astype(np.float64)
+        for k in range(C):
+            loc = int(crit[k]) - row_offset
+            if 0 <= loc < x.shape[0]:
+                dQ[loc] += dqm.numpy()[k]
+        f32 = lambda v: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
+        if p.nonlinear:
+            h1 = H1.numpy()
+            dz2 = dQ * (1 - q * q)
+            dz1 = (dz2 @ p.W2) * (h1 > 0)
+            return f32(dz1.T @ x), f32(dz1.sum(0)), f32(dz2.T @ h1), f32(dz2.sum(0))
+        return f32(dQ.T @ x), f32(dQ.sum(0)), None, None
+
+
+def _train_worker(rank, world, port, name, N_override, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from helpers import build_net
+        from dsmil_wsi_b200.sharded import shard_bounds, sharded_caller_loss, sharded_milnet_forward
+        g, p, X = load_golden(name)
+        if N_override is not None:
+            X = X[:N_override]
+        lo, hi = shard_bounds(X.shape[0], world)[rank]
+        net = build_net(p, device="cpu")
+        y = torch.from_numpy(np.asarray(g["y"], np.float32).reshape(-1))
+        classes, pred, A, B, crit = sharded_milnet_forward(net, torch.from_numpy(X[lo:hi]), lo, ops=OracleTrainOps(p))
+        loss = sharded_caller_loss(classes, pred, crit, lo, y, torch.nn.BCEWithLogitsLoss())
+        loss.backward()
+        ret[rank] = dict(loss=float(loss.detach()), grads={k: v.grad.numpy().copy() for k, v in net.named_parameters()
+                                                  if v.grad is not None})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,name,N_override", [(2, "shipped_tcga", None), (3, "lin_d512_c3", None),
+                                                   (2, "musk_d166_n7", None), (2, "musk_d166_n7", 1)])
+def test_sharded_training_step_over_gloo(world, name, N_override):
+    """Every rank ends with the single-device gradients of the callers' loss (train_tcga.py:67-72), and the same
+    loss value: three all-reduces in the reverse pass, one all-reduce(max) in the loss."""
+    from helpers import grad_name
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_train_worker, args=(world, port, name, N_override, ret), nprocs=world, join=True)
+    g, p, X = load_golden(name)
+    if N_override is not None:
+        X = X[:N_override]
+    one = orc.forward(X, p)
+    y = np.asarray(g["y"], np.float64).reshape(-1)
+    loss, d_cls, d_pred = orc.caller_loss_grads(one, y)
+    ref = orc.backward(X, p, one, d_cls, d_pred)
+    for r in range(world):
+        assert abs(ret[r]["loss"] - loss) < 2e-6
+        grads = ret[r]["grads"]
+        for short, want in ref.items():
+            got = grads[grad_name(short, p.nonlinear)]
+            # the forward's records travel as fp32 (A to ~2e-6); the softmax backward amplifies that a few times
+            assert got.shape == want.shape
+            if np.abs(want).max() < 1e-12:      # N == 1: A == 1, dL == 0 exactly, the q-branch gets no gradient
+                assert np.abs(got).max() < 1e-7, (r, short)
+            else:
+                assert rel_to_max(got, want) < 5e-5, (r, short)
+        for k in grads:                                              # replicated bit for bit
+            assert np.array_equal(grads[k], ret[0]["grads"][k]), k
+
+
+@pytest.mark.parametrize("name,G", [("shipped_tcga", 3), ("lin_d512_c3", 4), ("musk_d166_n7", 8), ("musk_d166_n1", 2)])
+def test_virtual_sharded_train_step_host_logic(name, G):
+    """The single-device validation helper (reductions as local sums) with the oracle-backed ops: same indexing
+    and record plumbing the GPU test (tests/test_zz_shard_backward_gpu.py) relies on."""
+    from dsmil_wsi_b200.sharded import virtual_sharded_train_step
+    g, p, X = load_golden(name)
+    one = orc.forward(X, p)
+    y = np.asarray(g["y"], np.float64).reshape(-1)
+    _, d_cls, d_pred = orc.caller_loss_grads(one, y)
+    ref = orc.backward(X, p, one, d_cls, d_pred)
+    grads_of = lambda classes, pred: (torch.from_numpy(d_cls), torch.from_numpy(d_pred))
+    outs, grads = virtual_sharded_train_step(OracleTrainOps(p), torch.from_numpy(X), G, grads_of)
+    assert np.array_equal(outs[4].numpy(), one.idx) and rel_to_max(outs[2].numpy(), one.A) < 2e-6
+    for short, got in zip(["Wi", "bi", "W1", "b1", "W2", "b2", "Wf", "bf"], grads):
+        if got is None:
+            assert not p.nonlinear and short in ("W2", "b2")
+        elif np.abs(ref[short]).max() < 1e-12:
+            assert np.abs(got.numpy()).max() < 1e-7
+        else:
+            assert rel_to_max(got.numpy(), ref[short]) < 5e-5, short
