@@ -268,3 +268,52 @@ def test_virtual_sharded_train_step_host_logic(name, G):
             assert np.abs(got.numpy()).max() < 1e-7
         else:
             assert rel_to_max(got.numpy(), ref[short]) < 5e-5, short
+
+
+# ---- a batch of row-sharded bags: two collectives per STEP (records packed per bag) ------------------------------
+
+
+def _bags_worker(rank, world, port, sizes, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dsmil_wsi_b200.sharded import shard_bounds, sharded_forward_bags
+        p = orc.random_params(64, 3, 21, scale=1.5)
+        ops = OracleShardOps(p)
+        xs, offs = [], []
+        for i, n in enumerate(sizes):
+            X = orc.synthetic_bag(n, 64, 300 + i, "normal")
+            lo, hi = shard_bounds(n, world)[rank]
+            xs.append(torch.from_numpy(X[lo:hi]))
+            offs.append(lo)
+        n_coll = {"n": 0}
+        real = dist.all_gather_into_tensor
+
+        def counting(*a, **k):
+            n_coll["n"] += 1
+            return real(*a, **k)
+        dist.all_gather_into_tensor = counting
+        outs = sharded_forward_bags(ops, xs, offs)
+        ret[rank] = dict(collectives=n_coll["n"], offs=offs,
+                         outs=[tuple(t.numpy() for t in o) for o in outs])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,sizes", [(2, [37, 5, 120]), (3, [2, 64, 9, 1])])
+def test_sharded_bags_two_collectives_per_step(world, sizes):
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_bags_worker, args=(world, port, sizes, ret), nprocs=world, join=True)
+    p = orc.random_params(64, 3, 21, scale=1.5)
+    for r in range(world):
+        assert ret[r]["collectives"] == 2                      # not two per bag
+        for i, n in enumerate(sizes):
+            one = orc.forward(orc.synthetic_bag(n, 64, 300 + i, "normal"), p)
+            classes, pred, A, B, crit = ret[r]["outs"][i]
+            lo = ret[r]["offs"][i]
+            assert np.array_equal(crit, one.idx)
+            assert rel_to_max(pred, one.prediction_bag) < 2e-6 and rel_to_max(B, one.B) < 2e-6
+            if classes.shape[0]:
+                assert rel_to_max(classes, one.classes[lo:lo + classes.shape[0]]) < 1e-12
+                assert rel_to_max(A, one.A[lo:lo + A.shape[0]]) < 2e-6
