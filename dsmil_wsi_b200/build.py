@@ -13,6 +13,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdsmil_b200.so")
 SOURCES = ["abi.cu"]
+HOST_CSRC = os.path.join(HERE, "csrc_host")
+HOST_LIB = os.path.join(LIBDIR, "libdsmil_host.so")
+HOST_SOURCES = ["bagcsv.c"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -55,5 +58,35 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+def _host_digest():
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(HOST_CSRC)):
+        h.update(f.encode())
+        h.update(open(os.path.join(HOST_CSRC, f), "rb").read())
+    return h.hexdigest()
+
+
+def build_host_library(force=False):
+    """libdsmil_host.so: host-only C (bag CSV reader / writer, csrc_host/), plain gcc -- no CUDA in it."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    stamp = os.path.join(LIBDIR, ".build_digest_host")
+    dig = _host_digest()
+    if not force and os.path.exists(HOST_LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return HOST_LIB
+    cc = os.environ.get("CC") or shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        raise RuntimeError("no C compiler found (set CC=/path/to/gcc)")
+    cmd = [cc, "-O3", "-std=c11", "-Wall", "-Wextra", "-shared", "-fPIC", "-o", HOST_LIB] + \
+          [os.path.join(HOST_CSRC, s) for s in HOST_SOURCES] + ["-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("gcc failed building libdsmil_host.so")
+    with open(stamp, "w") as f:
+        f.write(dig)
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host_library(force="--force" in sys.argv))

@@ -185,3 +185,80 @@ def test_container_writer_of_the_embedding_loop(tmp_path):
     exact, _ = F.read_bag_bin(p_bin)
     assert np.array_equal(exact.numpy(), feats)                        # lossless
     assert np.abs(F.read_bag_csv(p_csv) - feats).max() <= 5.1e-5       # the CSV keeps 4 decimals
+
+
+# ---- native bag-CSV reader / writer (csrc_host/bagcsv.c) vs the reference's pandas route --------------------------
+
+
+def _py_format(feats):
+    lines = [",".join(str(i) for i in range(feats.shape[1]))]
+    lines += [",".join("%.4f" % v for v in row) for row in feats]
+    return "\n".join(lines) + "\n"
+
+
+def test_native_writer_is_python_percent_4f_for_every_float32_it_meets():
+    """'%.4f' % float(v): exact decimal of the binary value, ties to even, sign of -0.0000 kept."""
+    from dsmil_wsi_b200.embed import format_bag_csv
+    rng = np.random.default_rng(0)
+    bits = rng.integers(0, 2 ** 32, size=120_000, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    bits = bits[np.isfinite(bits)]
+    k = rng.integers(0, 200_000, size=40_000)
+    vals = np.concatenate([
+        bits,                                                          # any finite float32 incl. denormals, 1e38
+        (np.abs(rng.standard_normal(60_000)) * 2).astype(np.float32),  # the range features live in
+        ((2 * k + 1) / 20000.0).astype(np.float32),                    # neighbours of the x.xxxx5 ties
+        np.array([0.0, -0.0, 0.00005, 0.00015, -0.00005, 0.99995, 12345.678, 2.0 ** 39, -2.0 ** 39, 2.0 ** 40,
+                  3.4e38, 1e-45, np.inf, -np.inf], np.float32)])
+    vals = vals[: vals.size // 7 * 7].reshape(-1, 7)
+    assert format_bag_csv(vals) == _py_format(vals)
+
+
+def test_native_writer_matches_pandas_text_and_nan_convention(tmp_path):
+    import pandas as pd
+    from dsmil_wsi_b200.embed import format_bag_csv, write_bag_csv
+    rng = np.random.default_rng(1)
+    feats = (rng.standard_normal((333, 17)) * np.array([1e-5, 1, 10, 1000] * 4 + [1e6])).astype(np.float32)
+    feats[3, 4] = np.nan                                               # pandas writes an empty field
+    feats[0, 0], feats[1, 1] = 0.0, -0.00004
+    buf = __import__("io").StringIO()
+    pd.DataFrame(feats).to_csv(buf, index=False, float_format="%.4f")
+    assert format_bag_csv(feats) == buf.getvalue()
+    p = write_bag_csv(feats, str(tmp_path), os.path.join("WSI", "ds", "single", "c0", "s1"))
+    assert open(p).read() == buf.getvalue()
+    for N in (0, 1):                                                    # degenerate bags still get the header
+        buf = __import__("io").StringIO()
+        pd.DataFrame(np.zeros((N, 5), np.float32), columns=range(5)).to_csv(buf, index=False, float_format="%.4f")
+        assert format_bag_csv(np.zeros((N, 5), np.float32)) == buf.getvalue()
+
+
+@pytest.mark.parametrize("N,D", [(1, 1), (50, 512), (1000, 7)])
+def test_native_reader_is_bit_identical_to_the_pandas_route(tmp_path, N, D):
+    from dsmil_wsi_b200.embed import format_bag_csv
+    rng = np.random.default_rng(N + D)
+    feats = (np.abs(rng.standard_normal((N, D))) * rng.choice([1e-3, 1.0, 50.0, 2e4], size=(N, D))).astype(np.float32)
+    p = str(tmp_path / "bag.csv")
+    open(p, "w").write(format_bag_csv(feats))
+    a, b = F.read_bag_csv(p), F.read_bag_csv(p, engine="pandas")
+    assert a.dtype == np.float32 and a.shape == (N, D) and np.array_equal(a, b)
+    assert np.abs(a - feats).max() <= 5.1e-5 * max(1.0, np.abs(feats).max())
+    out = np.full(N * D + 3, -1, np.float32)
+    c = F.read_bag_csv(p, out=out)
+    assert np.shares_memory(c, out) and np.array_equal(c, a) and (out[N * D:] == -1).all()
+
+
+def test_native_reader_general_fields_and_errors(tmp_path):
+    """Hand-written CSVs: exponents, signs, long mantissas, CRLF, blank lines, empty fields -- against pandas."""
+    text = "0,1,2\r\n1e-3,-2.5E+2,+7\r\n\r\n0.1234567890123456789,123456789012345678901,.5\r\n,3.,-0\r\n"
+    p = str(tmp_path / "odd.csv")
+    open(p, "w", newline="").write(text)
+    a, b = F.read_bag_csv(p), F.read_bag_csv(p, engine="pandas")
+    assert a.shape == b.shape == (3, 3)
+    assert np.array_equal(a, b, equal_nan=True) and np.isnan(a[2, 0]) and np.signbit(a[2, 2])
+    for bad, needle in (("0,1\n1,2,3\n", "ragged"), ("0,1\n1\n", "ragged"), ("0,1\n1,abc\n", "not a number"),
+                        ("", "not a bag CSV")):
+        q = str(tmp_path / "bad.csv")
+        open(q, "w").write(bad)
+        with pytest.raises(ValueError, match=needle):
+            F.read_bag_csv(q)
+    with pytest.raises(ValueError, match="engine"):
+        F.read_bag_csv(p, engine="polars")
