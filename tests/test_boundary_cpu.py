@@ -119,3 +119,16 @@ def test_library_exports_every_declared_symbol():
     assert lib.dsmil_backward_workspace_bytes(ctypes.byref(P), 10000, 0) > 0
     bad = _lib.DsmilParams(512, 99, 1, 0)
     assert lib.dsmil_forward_workspace_bytes(ctypes.byref(bad), 10) == 0
+
+
+def test_host_library_exports_every_declared_symbol():
+    """include/dsmil_host.h <-> libdsmil_host.so <-> _hostlib.SIGNATURES."""
+    import re
+    from dsmil_wsi_b200 import _hostlib
+    hdr = open(os.path.join(ROOT, "include", "dsmil_host.h")).read()
+    declared = set(re.findall(r"\b(dsmil_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_hostlib.SIGNATURES), declared ^ set(_hostlib.SIGNATURES)
+    lib = _hostlib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.dsmil_host_abi_version() == 1 and "#define DSMIL_HOST_ABI_VERSION 1" in hdr
