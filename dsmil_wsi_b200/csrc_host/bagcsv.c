@@ -147,20 +147,21 @@ int64_t dsmil_csv_write_bag(const char* path, const float* x, int64_t N, int32_t
 /* Columns of the header line and number of non-blank data lines.  Returns 0 or a negative error. */
 int32_t dsmil_csv_shape(const char* buf, int64_t len, int64_t* N, int32_t* D) {
   if (!buf || len < 0 || !N || !D) return DSMIL_CSV_ERR_ARG;
-  int64_t i = 0;
+  const char* const end = buf + len;
+  const char* nl = (const char*)memchr(buf, '\n', (size_t)len);
+  const char* hend = nl ? nl : end;
+  if (hend == buf || (hend == buf + 1 && buf[0] == '\r')) return DSMIL_CSV_ERR_ARG;   /* no header */
   int32_t cols = 1;
-  while (i < len && buf[i] != '\n') { if (buf[i] == ',') ++cols; ++i; }
-  if (i == 0 || (i == 1 && buf[0] == '\r')) return DSMIL_CSV_ERR_ARG;       /* no header */
+  for (const char* p = buf; p < hend; ++p) cols += (*p == ',');
   *D = cols;
   int64_t rows = 0;
-  ++i;
-  while (i < len) {
-    int64_t j = i;
-    while (j < len && buf[j] != '\n') ++j;
-    int64_t e = j;
-    if (e > i && buf[e - 1] == '\r') --e;
-    if (e > i) ++rows;                                                       /* blank lines are skipped */
-    i = j + 1;
+  const char* p = nl ? nl + 1 : end;
+  while (p < end) {
+    const char* q = (const char*)memchr(p, '\n', (size_t)(end - p));
+    const char* e = q ? q : end;
+    if (e > p && e[-1] == '\r') --e;
+    if (e > p) ++rows;                                                       /* blank lines are skipped */
+    p = q ? q + 1 : end;
   }
   *N = rows;
   return 0;
@@ -208,34 +209,67 @@ static inline int parse_field(const char* s, const char* e, float* out) {
  * or a bad number the 1-based data-line number is stored in *bad_line. */
 int32_t dsmil_csv_parse_bag(const char* buf, int64_t len, float* out, int64_t N, int32_t D, int64_t* bad_line) {
   if (!buf || len < 0 || (!out && N > 0) || N < 0 || D < 1) return DSMIL_CSV_ERR_ARG;
-  int64_t i = 0;
-  while (i < len && buf[i] != '\n') ++i;                                     /* skip the header */
-  ++i;
+  const char* const end = buf + len;
+  const char* p = (const char*)memchr(buf, '\n', (size_t)len);              /* skip the header */
+  p = p ? p + 1 : end;
   int64_t row = 0;
-  while (i < len) {
-    int64_t j = i;
-    while (j < len && buf[j] != '\n') ++j;
-    int64_t e = j;
-    if (e > i && buf[e - 1] == '\r') --e;
-    if (e > i) {
-      if (row >= N) { if (bad_line) *bad_line = row + 1; return DSMIL_CSV_ERR_RAGGED; }
-      float* dst = out + row * D;
-      int32_t col = 0;
-      int64_t s = i;
-      for (int64_t k = i; k <= e; ++k) {
-        if (k == e || buf[k] == ',') {
-          if (col >= D) { if (bad_line) *bad_line = row + 1; return DSMIL_CSV_ERR_RAGGED; }
-          const int rc = parse_field(buf + s, buf + k, dst + col);
-          if (rc) { if (bad_line) *bad_line = row + 1; return rc; }
-          ++col;
-          s = k + 1;
+#define DSMIL_CSV_FAIL(code, line) do { if (bad_line) *bad_line = (line); return (code); } while (0)
+  while (p < end) {
+    if (*p == '\n') { ++p; continue; }                                       /* blank line */
+    if (*p == '\r' && p + 1 < end && p[1] == '\n') { p += 2; continue; }
+    if (*p == '\r' && p + 1 == end) break;
+    if (row >= N) DSMIL_CSV_FAIL(DSMIL_CSV_ERR_RAGGED, row + 1);
+    float* dst = out + row * D;
+    int32_t col = 0;
+    for (;;) {                                                               /* one field per iteration */
+      if (col >= D) DSMIL_CSV_FAIL(DSMIL_CSV_ERR_RAGGED, row + 1);
+      /* fast path: [sign] digits [. digits] with at most 18 significant digits, ended by , \r \n or EOF */
+      const char* q = p;
+      int neg = 0;
+      if (q < end && (*q == '-' || *q == '+')) { neg = (*q == '-'); ++q; }
+      uint64_t K = 0;
+      int digits = 0, frac = 0, any = 0;
+      while (q < end && (unsigned)(*q - '0') < 10u && digits < 18) {
+        K = K * 10 + (uint64_t)(*q - '0');
+        digits += (K != 0 || digits != 0);
+        any = 1;
+        ++q;
+      }
+      if (q < end && *q == '.') {
+        ++q;
+        while (q < end && (unsigned)(*q - '0') < 10u && digits < 18) {
+          K = K * 10 + (uint64_t)(*q - '0');
+          digits += (K != 0 || digits != 0);
+          ++frac;
+          any = 1;
+          ++q;
         }
       }
-      if (col != D) { if (bad_line) *bad_line = row + 1; return DSMIL_CSV_ERR_RAGGED; }
-      ++row;
+      const int at_end = (q == end) || *q == ',' || *q == '\n' || *q == '\r';
+      if (at_end && any && K < (UINT64_C(1) << 53) && frac <= 22) {
+        const double d = (double)K / kPow10[frac];
+        dst[col] = (float)(neg ? -d : d);
+      } else {                                                               /* general path on the whole field */
+        const char* e = p;
+        while (e < end && *e != ',' && *e != '\n' && *e != '\r') ++e;
+        const int rc = parse_field(p, e, dst + col);
+        if (rc) DSMIL_CSV_FAIL(rc, row + 1);
+        q = e;
+      }
+      ++col;
+      p = q;
+      if (p < end && *p == ',') { ++p; continue; }
+      break;                                                                 /* end of line or of file */
     }
-    i = j + 1;
+    if (p < end && *p == '\r') ++p;
+    if (p < end) {
+      if (*p != '\n') DSMIL_CSV_FAIL(DSMIL_CSV_ERR_NUMBER, row + 1);
+      ++p;
+    }
+    if (col != D) DSMIL_CSV_FAIL(DSMIL_CSV_ERR_RAGGED, row + 1);
+    ++row;
   }
+#undef DSMIL_CSV_FAIL
   if (row != N) { if (bad_line) *bad_line = row; return DSMIL_CSV_ERR_RAGGED; }
   return 0;
 }
