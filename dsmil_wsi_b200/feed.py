@@ -74,13 +74,16 @@ class DeviceBagStore:
         if pin:
             torch.cuda.current_stream(self.device).synchronize()   # pinned sources may be freed after this
 
-    def add_index(self, index_csv: str, num_classes: int, tcga_default: bool = False) -> None:
-        """The reference's route (train_tcga.py:245-250 + :36-51) without the temp_train/*.pt detour."""
+    def add_index(self, index_csv: str, num_classes: int, tcga_default: bool = False, workers: int = 4) -> None:
+        """The reference's route (train_tcga.py:245-250 + :36-51) without the temp_train/*.pt detour.  Bag CSVs
+        are parsed by the native reader on `workers` threads (the C call releases the GIL), in index order."""
+        from concurrent.futures import ThreadPoolExecutor
         from . import formats
-        for entry, label in formats.read_dataset_index(index_csv):
-            csv = formats.tcga_default_feats_path(entry) if tcga_default else entry
-            self.add_bag(torch.from_numpy(formats.read_bag_csv(csv)),
-                         torch.from_numpy(formats.bag_label(label, num_classes)))
+        rows = formats.read_dataset_index(index_csv)
+        paths = [formats.tcga_default_feats_path(e) if tcga_default else e for e, _ in rows]
+        with ThreadPoolExecutor(max_workers=max(1, workers)) as pool:
+            for feats, (_, label) in zip(pool.map(formats.read_bag_csv, paths), rows):
+                self.add_bag(torch.from_numpy(feats), torch.from_numpy(formats.bag_label(label, num_classes)))
 
     def __len__(self):
         return len(self.bags)
