@@ -262,3 +262,23 @@ def test_native_reader_general_fields_and_errors(tmp_path):
             F.read_bag_csv(q)
     with pytest.raises(ValueError, match="engine"):
         F.read_bag_csv(p, engine="polars")
+
+
+def test_native_reader_fast_path_is_correctly_rounded(tmp_path):
+    """Fields of up to 18 significant digits: float32(correctly rounded double) == np.float32(float(text))."""
+    rng = np.random.default_rng(5)
+    fields = []
+    for _ in range(20_000):
+        nd = int(rng.integers(1, 19))
+        digits = "".join(str(d) for d in rng.integers(0, 10, size=nd))
+        cut = int(rng.integers(0, nd + 1))
+        text = (digits[:cut] or "0") + ("." + digits[cut:] if cut < nd else "")
+        fields.append(("-" if rng.random() < 0.3 else "") + text)
+    D = 8
+    rows = [fields[i:i + D] for i in range(0, len(fields), D)]
+    p = str(tmp_path / "f.csv")
+    open(p, "w").write(",".join(str(i) for i in range(D)) + "\n" + "\n".join(",".join(r) for r in rows) + "\n")
+    got = F.read_bag_csv(p)
+    want = np.array([[np.float32(float(t)) for t in r] for r in rows], dtype=np.float32)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert np.array_equal(np.signbit(got), np.signbit(want))
