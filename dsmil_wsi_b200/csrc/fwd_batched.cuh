@@ -29,8 +29,11 @@ struct AttendArgs {
 };
 
 // CT = classes rounded up to 1,2,4; NJ = float4 column groups per thread (D <= 512*NJ)
+// Occupancy: the D <= 512, C <= 2 instantiations fit 48 registers without spills, i.e. 5 CTAs per SM instead of 4.
+// One CTA per 128-row tile makes the 16 x 10 000-row step 1264 CTAs: 2.14 waves of 592 slots (three rounds) become
+// 1.71 waves of 740 (two rounds) -- see DESIGN.md §8-1b.  Wider variants keep the default bound (they would spill).
 template <int CT, int NJ>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NJ == 1 && CT <= 2) ? 5 : 0)
 k_attend_b(const AttendArgs a) {
   extern __shared__ __align__(16) float s_dyn[];           // [C][D] cross-half reduction buffer
   __shared__ __align__(16) float sq[CT][kQ];
