@@ -12,9 +12,15 @@ N GPUs  : weak scaling -- every bag is a giant bag of 10 000*N rows row-sharded 
 value   : whole-job patches/sec, inputs resident in HBM, CUDA-event timed, max over ranks.
 e2e     : same metric through the public host-buffer API (dsmil_wsi_b200.pipeline.HostBagPipeline):
           pinned host bags -> H2D -> forward -> D2H of (classes, prediction_bag, A, B), per step.
-roofline: dominant kernel's algorithmic bytes / its CUDA-event duration vs MEASURED_PEAKS.json.
-cpu_baseline: the oracle's torch-CPU port of the reference op sequence on the host cores (bounded sample).
-`--impl reference` times that CPU port alone (the reference is pure PyTorch).
+roofline: frac = algorithmic bytes of the WHOLE forward step / CUDA-event step time / measured HBM peak
+          (MEASURED_PEAKS.json); `dominant_kernel_frac` is the same bytes over the dominant kernel alone;
+          `tensor_fraction` = bf16 tensor FLOPs issued (3xBF16: 3 products per GEMM) / step time / measured peak.
+cpu_baseline: the reference's own MILNet (oracle/_ref/dsmil.py, staged unmodified by build(); kind
+          "reference") or, when not staged, the oracle's torch-CPU port (kind "port") on a bounded sample.
+extras  : torch_eager_gpu (the unmodified reference module through PyTorch eager on the same GPU = the kernel
+          to beat), single-call milnet(x) latency, N=8 192 forward, N=15 000 C=1 forward+backward+Adam
+          (train_tcga.py:67-73), and the N=100 000 giant-bag STRONG-scaling workload (BASELINE configs 1,2,4).
+`--impl reference` times the reference's CPU implementation alone.
 """
 import argparse
 import ctypes
@@ -39,6 +45,48 @@ def algorithmic_bytes_fwd(N, D_, C_):
     """one read of X, write classes + A, weights once, B and pred."""
     W = 4 * (C_ * D_ + C_ + 128 * D_ + 128 + 128 * 128 + 128 + C_ * C_ * D_ + C_)
     return N * (4 * D_ + 8 * C_) + W + 4 * C_ * D_ + 4 * C_
+
+
+def tensor_flops_fwd(N, D_, issued=True):
+    """bf16 tensor-core FLOPs of the Q-MLP for N rows: 2*N*(D*128 + 128*128), x3 for the three split products
+    the kernel issues (hi*Whi + lo*Whi + hi*Wlo)."""
+    return (3 if issued else 1) * 2.0 * N * (D_ * 128 + 128 * 128)
+
+
+def load_reference_module():
+    """The UNMODIFIED reference dsmil.py staged in oracle/_ref (bench baseline legs only)."""
+    try:
+        from oracle import stage_ref
+        return stage_ref.load_reference_dsmil()
+    except Exception:
+        return None
+
+
+def make_reference_net(refmod, p, device, D_=None, C_=None):
+    """Reference MILNet(FCLayer, BClassifier) holding the benchmark weights (or random init for other shapes)."""
+    D_, C_ = D_ or D, C_ or C
+    net = refmod.MILNet(refmod.FCLayer(D_, C_), refmod.BClassifier(D_, C_))
+    if p is not None:
+        t = lambda a: torch.from_numpy(np.array(a, dtype=np.float32))
+        net.load_state_dict({"i_classifier.fc.0.weight": t(p.Wi), "i_classifier.fc.0.bias": t(p.bi),
+                             "b_classifier.q.0.weight": t(p.W1), "b_classifier.q.0.bias": t(p.b1),
+                             "b_classifier.q.2.weight": t(p.W2), "b_classifier.q.2.bias": t(p.b2),
+                             "b_classifier.fcc.weight": t(p.Wf), "b_classifier.fcc.bias": t(p.bf)})
+    return net.to(device)
+
+
+def cuda_time_ms(fn, reps, warm=3):
+    """Mean CUDA-event time of fn() over `reps` calls on the current stream (after `warm` untimed calls)."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
 
 
 def load_peaks():
@@ -140,61 +188,83 @@ def make_net(p, device):
     return net.to(device).eval()
 
 
+class CpuArm:
+    """The reference's CPU implementation of the path: its own MILNet (oracle/_ref/dsmil.py, unmodified, eval +
+    no_grad) when staged -- kind "reference" -- else the oracle's torch-CPU port -- kind "port"."""
+
+    def __init__(self, p, threads):
+        self.threads = threads
+        torch.set_num_threads(threads)
+        refmod = load_reference_module()
+        if refmod is not None:
+            self.kind = "reference"
+            self.net = make_reference_net(refmod, p, "cpu").eval()
+            self.what = "unmodified reference dsmil.MILNet (oracle/_ref/dsmil.py:64-74), torch-CPU fp32, eval + no_grad"
+        else:
+            from oracle import dsmil_oracle as orc
+            self.kind = "port"
+            self.port = orc.TorchPort(oracle_params(p), threads=threads)
+            self.what = "torch-CPU fp32 port of dsmil.py:46-62 (oracle/dsmil_oracle.py TorchPort)"
+
+    def forward(self, x):
+        if self.kind == "reference":
+            with torch.no_grad():
+                return self.net(x)
+        return self.port.forward(x)
+
+
 def best_cpu_threads(p, bags, budget=0.6):
     """torch-CPU with one thread per core is NOT the fastest setting on a many-core host for ops this
     small; give the baseline the thread count it likes best (short calibration, reported as `cores`)."""
-    from oracle import dsmil_oracle as orc
     ncpu = os.cpu_count() or 1
     cands = sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu})
     best, best_rate = cands[0], 0.0
     for c in cands:
-        port = orc.TorchPort(oracle_params(p), threads=c)
-        port.forward(bags[0])
+        arm = CpuArm(p, c)
+        arm.forward(bags[0])
         t0 = time.perf_counter(); n = 0
         while time.perf_counter() - t0 < budget:
-            port.forward(bags[n % len(bags)]); n += 1
+            arm.forward(bags[n % len(bags)]); n += 1
         rate = n / (time.perf_counter() - t0)
         if rate > best_rate:
             best, best_rate = c, rate
     return best
 
 
-def cpu_port_rate(p, seconds, threads=None, nbags=4):
-    """Oracle torch-CPU port (reference op sequence) on a bounded sample: returns patches/s."""
-    from oracle import dsmil_oracle as orc
+def cpu_port_rate(p, seconds, threads=None, nbags=16):
+    """CPU arm on a bounded sample (distinct bags cycled, like the GPU arm's step): returns patches/s."""
     g = torch.Generator().manual_seed(1)
     bags = [torch.rand(NBAG, D, generator=g) for _ in range(nbags)]
-    threads = threads or best_cpu_threads(p, bags)
-    port = orc.TorchPort(oracle_params(p), threads=threads)
+    threads = threads or best_cpu_threads(p, bags[:4])
+    arm = CpuArm(p, threads)
     for b in bags[:2]:
-        port.forward(b)
+        arm.forward(b)
     t0 = time.perf_counter()
     n = 0
     while time.perf_counter() - t0 < seconds:
-        port.forward(bags[n % nbags])
+        arm.forward(bags[n % nbags])
         n += 1
     dt = time.perf_counter() - t0
-    return n * NBAG / dt, port.threads, n
+    return n * NBAG / dt, arm, n
 
 
 def run_reference(args):
-    """`--impl reference`: the reference is pure PyTorch, so its CPU implementation of the path is the
-    torch-CPU op sequence of dsmil.py; timed here via the oracle port (no /root/reference on the box)."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores -- the unmodified
+    reference module staged in oracle/_ref when present (kind "reference"), else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import dsmil_oracle as orc
     g = torch.Generator().manual_seed(1)
     nb = args.ref_bags
     bags = [torch.rand(NBAG, D, generator=g) for _ in range(nb)]
-    port = orc.TorchPort(oracle_params(make_params()), threads=best_cpu_threads(make_params(), bags[:4]))
+    arm = CpuArm(make_params(), best_cpu_threads(make_params(), bags[:4]))
     for _ in range(max(args.warmup, 1)):
         for b in bags:
-            port.forward(b)
+            arm.forward(b)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for b in bags:
-            port.forward(b)
+            arm.forward(b)
     dt = time.perf_counter() - t0
     val = args.steps * nb * NBAG / dt
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "patches/s", "n_gpus": args.gpus,
@@ -202,11 +272,77 @@ def run_reference(args):
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"stream of {nb} synthetic bags, each N={NBAG} x D={D}, C={C}, DSMIL forward "
                                   "(bounded sample of the GPU arm's 16-bag step)", "bags_per_step": nb},
-           "cpu_baseline": {"value": val, "unit": "patches/s", "cores": port.threads, "kind": "port",
-                            "sample": f"{args.steps} steps x {nb} bags x {NBAG} patches, torch-CPU fp32, all host threads"},
+           "cpu_baseline": {"value": val, "unit": "patches/s", "cores": arm.threads, "kind": arm.kind,
+                            "sample": f"{args.steps} steps x {nb} bags x {NBAG} patches; {arm.what}; all host threads "
+                                      f"it scales to ({arm.threads})"},
            "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
+
+
+def run_extras(args, p, net, bags, dev, ms_per_step):
+    """Rank 0, one GPU: the other BASELINE configs and the 'kernel to beat' (same box, same run)."""
+    import dsmil as mil
+    ex = {}
+    refmod = load_reference_module()
+    nb = len(bags)
+    # (1) the unmodified reference module through PyTorch eager on this GPU, same bags, same weights
+    if refmod is not None:
+        rnet = make_reference_net(refmod, p, dev).eval()
+
+        def eager_step():
+            with torch.no_grad():
+                for b in bags:
+                    rnet(b)
+        ms = cuda_time_ms(eager_step, 5, warm=2)
+        ex["torch_eager_gpu"] = {"value": nb * NBAG / (ms / 1e3), "unit": "patches/s", "ms_per_step": ms,
+                                 "what": "oracle/_ref/dsmil.py MILNet (unmodified reference), eval + no_grad, PyTorch eager "
+                                         "on cuda:0, same 16 bags and weights", "speedup_device_timed": ms / ms_per_step}
+    else:
+        rnet = None
+        ex["torch_eager_gpu"] = {"unavailable": "reference sources not staged in oracle/_ref"}
+    # (2) the call the reference's drivers make: ONE bag through milnet(x)  (train_tcga.py:98)
+    with torch.no_grad():
+        one = cuda_time_ms(lambda: net(bags[0]), 50, warm=5)
+        ex["single_call_n10000"] = {"ms": one, "patches_per_s": NBAG / (one / 1e3), "api": "milnet(x), eval, no_grad"}
+        if rnet is not None:
+            r1 = cuda_time_ms(lambda: rnet(bags[0]), 20, warm=3)
+            ex["single_call_n10000"].update({"torch_eager_gpu_ms": r1, "speedup": r1 / one})
+    # (3) BASELINE configs[1]: N=8 192 forward
+    g = torch.Generator(device=dev).manual_seed(7)
+    b8 = [torch.rand(8192, D, generator=g, device=dev) for _ in range(nb)]
+    with torch.no_grad():
+        ms8 = cuda_time_ms(lambda: net.forward_bags(b8), 20, warm=3)
+    ex["fwd_n8192"] = {"value": nb * 8192 / (ms8 / 1e3), "unit": "patches/s", "ms_per_step": ms8, "bags_per_step": nb,
+                       "hbm_frac": algorithmic_bytes_fwd(8192, D, C) * nb / (ms8 / 1e3) / 1e9 / load_peaks()[0]}
+    del b8
+    # (4) BASELINE configs[2]: Camelyon16 shape, N=15 000, C=1, forward + backward + Adam (train_tcga.py:67-73,232)
+    NT, CT_ = 15000, 1
+    tb = [torch.rand(NT, D, generator=g, device=dev) for _ in range(4)]
+    lab = torch.ones(1, CT_, device=dev)
+
+    def make_train(modlib):
+        torch.manual_seed(0)
+        m = modlib.MILNet(modlib.FCLayer(D, CT_), modlib.BClassifier(D, CT_)).to(dev).train()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-4, betas=(0.5, 0.9), weight_decay=1e-3)
+        crit = torch.nn.BCEWithLogitsLoss()
+        k = [0]
+
+        def tstep():
+            opt.zero_grad()
+            ins, bagp, _, _ = m(tb[k[0] % 4]); k[0] += 1
+            mx, _ = torch.max(ins, 0)
+            loss = 0.5 * crit(bagp.view(1, -1), lab) + 0.5 * crit(mx.view(1, -1), lab)
+            loss.backward()
+            opt.step()
+        return tstep
+    mst = cuda_time_ms(make_train(mil), 20, warm=3)
+    ex["train_n15000_c1"] = {"ms_per_step": mst, "patches_per_s": NT / (mst / 1e3), "slides_per_s": 1e3 / mst,
+                             "what": "milnet(x) -> 0.5*BCE(bag)+0.5*BCE(max) -> backward -> Adam, one bag per step"}
+    if refmod is not None:
+        msr = cuda_time_ms(make_train(refmod), 10, warm=3)
+        ex["train_n15000_c1"].update({"torch_eager_gpu_ms": msr, "speedup": msr / mst})
+    return ex
 
 
 def run_ours(args):
@@ -297,7 +433,7 @@ def run_ours(args):
     patches_per_step = nb * NBAG * world
     value = patches_per_step / (ms_per_step / 1e3)
 
-    # ---- roofline of the dominant kernel, timed live with CUDA events on the launch stream -------
+    # ---- roofline: whole forward step (headline) + the dominant kernel, timed live with CUDA events ----
     hbm_peak, tf_peak, peak_src = load_peaks()
     lib.dsmil_profile_enable(1)
     for _ in range(2):
@@ -312,24 +448,29 @@ def run_ours(args):
     dom = max((t for t in tags if per[t]), key=lambda t: per[t] * n_tag[tags.index(t)])
     launches_dom = int(n_tag[tags.index(dom)])
     bags_per_launch = 2.0 * nb / launches_dom          # 2 profiled steps of nb bags each
-    alg = algorithmic_bytes_fwd(NBAG, D, C) * bags_per_launch
+    alg_step = algorithmic_bytes_fwd(NBAG, D, C) * nb   # this rank's algorithmic bytes per step
     dom_ms = per[dom]
-    achieved = alg / (dom_ms / 1e3) / 1e9
+    achieved = alg_step / (ms_per_step / 1e3) / 1e9     # whole forward: every kernel and gap of the step is charged
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath):     # dram__bytes_read+write of the dominant kernel from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.exists(tpath):     # dram__bytes_read+write of the step's kernels from the committed ncu --set full capture
         tj = json.load(open(tpath))
-        if tj.get("tag") == dom:
-            traffic = tj["dram_bytes_per_row"] * NBAG * bags_per_launch
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg, "bags_per_launch": bags_per_launch, "kernel_ms": dom_ms,
+        traffic = tj.get("dram_bytes_per_step_16x10k")
+        if traffic is not None and nb != 16:
+            traffic = traffic * nb / 16.0
+    tflops = tensor_flops_fwd(NBAG * nb, D) / (ms_per_step / 1e3) / 1e12
+    roofline = {"bound": "hbm", "kernel": "whole forward step (all kernels of forward_bags)", "achieved": achieved,
+                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_step": alg_step,
+                "dominant_kernel": dom, "dominant_kernel_ms": dom_ms,
+                "dominant_kernel_frac": (algorithmic_bytes_fwd(NBAG, D, C) * bags_per_launch / (dom_ms / 1e3) / 1e9) / hbm_peak,
                 "per_kernel_ms": {k: v for k, v in per.items() if v},
-                "whole_forward_frac": (algorithmic_bytes_fwd(NBAG, D, C) * nb / (ms_per_step / 1e3) / 1e9) / hbm_peak,
-                "note": "achieved = algorithmic bytes of the whole fused forward (SURVEY 8d: 2048+8C B/patch + weights) for the "
-                        "bags one launch covers / the dominant kernel's mean CUDA-event duration; the forward is three "
-                        "kernels (phase 1 tcgen05 Q-MLP+scores, attend, finalize): whole_forward_frac charges all of them "
-                        "(CUDA-event time of the full step) and is the honest end-to-end roofline fraction"}
+                "tensor_fraction": tflops / tf_peak, "tensor_tflops_issued": tflops, "tensor_peak_tflops": tf_peak,
+                "tensor_fraction_algorithmic": tflops / 3.0 / tf_peak,
+                "note": "frac = algorithmic bytes of the forward (SURVEY 8d: 2048+8C B/patch + weights, x bags per step) / "
+                        "CUDA-event time of the whole step / measured HBM copy peak; dominant_kernel_frac charges only the "
+                        "dominant kernel's duration; tensor_fraction = bf16 FLOPs issued (3 split products per GEMM) / step "
+                        "time / measured bf16 peak (tensor_fraction_algorithmic counts each GEMM once)"}
 
     # ---- end to end through the public host-buffer API ------------------------------------------
     e2e = None
@@ -374,12 +515,78 @@ def run_ours(args):
                "d2h_bytes_per_step": 4 * (2 * NBAG * C + C + C * D) * nb * world, "ms_per_step": dt * 1e3,
                "api": "pinned host shards -> sharded_forward_bags -> host"}
 
+    # ---- giant-bag STRONG scaling (BASELINE configs[4], north_star ">= 6x at 8 GPUs on N=100 000"): the SAME bags at
+    # every world size, rows sharded over the ranks; value = total rows / max-over-ranks device time -------------
+    strong = None
+    if not args.no_extras:
+        NG, nbg = 100000, args.giant_bags
+        lo, hi = [(NG * r) // world for r in (rank, rank + 1)]
+        gg = torch.Generator(device=dev).manual_seed(4242)
+        giant = []
+        for _ in range(nbg):        # every rank draws the full bag from the same seed and keeps its slice
+            full = torch.rand(NG, D, generator=gg, device=dev)
+            giant.append(full[lo:hi].clone())
+            del full
+        goff = [lo] * nbg
+
+        def gstep():
+            with torch.no_grad():
+                if world == 1:
+                    return net.forward_bags(giant)
+                if bops is not None:
+                    return sharded_forward_bags_batched(bops, giant, goff)
+                return sharded_forward_bags(ops, giant, goff)
+        for _ in range(5):
+            gstep()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        greps = 20
+        g0.record()
+        for _ in range(greps):
+            gstep()
+        g1.record()
+        barrier()
+        gms = torch.tensor([g0.elapsed_time(g1) / greps], device=dev)
+        if world > 1:
+            dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        gms = float(gms.item())
+        galg = algorithmic_bytes_fwd(NG, D, C) * nbg
+        strong = {"workload": f"{nbg} giant bags x N={NG} x D={D}, C={C}, rows sharded over {world} GPU(s) "
+                              f"({hi - lo} rows/rank/bag); {nbg * NG * D * 4 / 1e6:.0f} MB of features in total (> L2)",
+                  "scaling": "strong", "value": nbg * NG / (gms / 1e3), "unit": "patches/s", "ms_per_step": gms,
+                  "n_gpus": world, "hbm_frac_per_gpu": galg / world / (gms / 1e3) / 1e9 / hbm_peak}
+        del giant
+
+    # ---- multi-rank parity check (outside every timed region): one sharded forward against the CPU oracle ------
+    parity = None
+    if world > 1 and not args.no_extras:
+        from oracle import dsmil_oracle as orc
+        Nc = 4096 * world + 37
+        xc = orc.synthetic_bag(Nc, D, 9, "uniform")
+        lo, hi = [(Nc * r) // world for r in (rank, rank + 1)]
+        xl = torch.from_numpy(xc[lo:hi]).to(dev)
+        with torch.no_grad():
+            o = (sharded_forward_bags_batched(bops, [xl], [lo]) if bops is not None
+                 else sharded_forward_bags(ops, [xl], [lo]))[0]
+        t = orc.forward(xc, oracle_params(p))      # fp64 truth of the same algebra
+        relmax = lambda a, b: float(np.max(np.abs(np.asarray(a, np.float64) - b)) / max(np.max(np.abs(b)), 1e-30))
+        mine = {"idx_equal": bool(np.array_equal(o[4].cpu().numpy().reshape(-1), t.idx)),
+                "classes": relmax(o[0].cpu().numpy(), t.classes[lo:hi]), "A": relmax(o[2].cpu().numpy(), t.A[lo:hi]),
+                "B": relmax(o[3].cpu().numpy().reshape(C, D), np.asarray(t.B).reshape(C, D)), "pred_abs": float(np.max(np.abs(o[1].cpu().numpy().reshape(-1) - t.prediction_bag.reshape(-1))))}
+        ok = mine["idx_equal"] and mine["classes"] < 2e-6 and mine["A"] < 2e-5 and mine["B"] < 1e-5
+        flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity = dict(mine, ok_all_ranks=bool(flag.item() == 1.0), N=Nc,
+                      checker="oracle/dsmil_oracle.py forward() on the full bag (fp32 restatement of dsmil.py:46-62)")
+
     cpu_baseline = None
+    extras = None
     if rank == 0 and world == 1:
-        rate, threads, nrun = cpu_port_rate(p, args.cpu_seconds)
-        cpu_baseline = {"value": rate, "unit": "patches/s", "cores": threads, "kind": "port",
-                        "sample": f"{nrun} forwards of one N={NBAG} bag in ~{args.cpu_seconds:.0f}s, torch-CPU fp32 "
-                                  "port of dsmil.py:46-62 (oracle/dsmil_oracle.py TorchPort)"}
+        rate, arm, nrun = cpu_port_rate(p, args.cpu_seconds)
+        cpu_baseline = {"value": rate, "unit": "patches/s", "cores": arm.threads, "kind": arm.kind,
+                        "sample": f"{nrun} forwards over 16 distinct N={NBAG} bags in ~{args.cpu_seconds:.0f}s; {arm.what}"}
+        if not args.no_extras:
+            extras = run_extras(args, p, net, bags, dev, ms_per_step)
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -392,7 +599,7 @@ def run_ours(args):
                           "l2_policy": f"inputs larger than L2: {nb} bags x {NBAG * D * 4 / 1e6:.1f} MB per rank cycled",
                           "forward_path": int(lib.dsmil_forward_path(ctypes.byref(_lib.DsmilParams(D, C, 1, 0)), NBAG))},
                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches * world,
-               "clocks": clocks}
+               "clocks": clocks, "strong_n100k": strong, "parity_check": parity, "extras": extras}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -407,6 +614,9 @@ def main():
     ap.add_argument("--bags", type=int, default=16, help="bags per step (16 x 20.5 MB > L2)")
     ap.add_argument("--ref-bags", type=int, default=16)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra workloads (eager-GPU baseline, N=8192, "
+                    "N=15000 training step, N=100k strong scaling, multi-rank parity check)")
+    ap.add_argument("--giant-bags", type=int, default=4, help="N=100 000 bags per step of the strong-scaling workload")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -552,10 +552,13 @@ size_t dsmil_forward_workspace_bytes(const dsmil_params_t* p, int64_t N) {
 size_t dsmil_forward_bags_workspace_bytes(const dsmil_params_t* p, const int64_t* Ns, int32_t nb) {
   if (!p || !Ns || nb < 1 || p->C < 1 || p->C > DSMIL_MAX_C || p->D < 1 || p->D > DSMIL_MAX_D) return 0;
   bool ok;
-  if (sm100::batched_supported(p)) return carve_bags(p, Ns, nb, true, nullptr, 0, &ok).bytes;
+  // dsmil_forward_bags may take either route (tensor-core batch, or the per-bag generic loop when
+  // DSMIL_B200_GENERIC=1 / a bag is not 16-byte aligned): the workspace must cover both layouts.
   int64_t mx = 0;
   for (int b = 0; b < nb; ++b) mx = std::max<int64_t>(mx, Ns[b]);
-  return carve_fwd(p, mx, nullptr, 0, &ok).bytes;
+  size_t bytes = carve_fwd(p, mx, nullptr, 0, &ok).bytes;
+  if (sm100::batched_supported(p)) bytes = std::max(bytes, carve_bags(p, Ns, nb, true, nullptr, 0, &ok).bytes);
+  return bytes;
 }
 
 int dsmil_forward_bags(const dsmil_params_t* p, const float* const* Xs, const int64_t* Ns, int32_t nb,
@@ -628,7 +631,9 @@ int dsmil_shard_phase1(const dsmil_params_t* p, const float* X, const float* x_f
     set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
     return DSMIL_ERR_WORKSPACE;
   }
-  float* h1 = p->nonlinear ? (H1 ? H1 : (use_sm100(p) ? nullptr : w.H1)) : nullptr;   // tc path keeps H1 in TMEM
+  // the tensor-core path keeps H1 in TMEM; the generic path (also taken for an unaligned X) needs a buffer
+  const bool tc = use_sm100(p) && w.wimg && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+  float* h1 = p->nonlinear ? (H1 ? H1 : (tc ? nullptr : w.H1)) : nullptr;
   return phase1_impl(p, X, x_for_v, classes_in, N_local, row_offset, classes, Q, h1, V, cand_rec, w.keys, w.wimg,
                      static_cast<cudaStream_t>(stream));
 }

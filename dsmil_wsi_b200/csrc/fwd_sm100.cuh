@@ -564,12 +564,10 @@ k_qmlp_sm100(const QmlpArgs a) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 bb = *reinterpret_cast<const float4*>(&s_b2[c0 + 4 * q]);
-            float4 o;
-            o.x = fast_tanh(__uint_as_float(v[4 * q + 0]) + bb.x);
-            o.y = fast_tanh(__uint_as_float(v[4 * q + 1]) + bb.y);
-            o.z = fast_tanh(__uint_as_float(v[4 * q + 2]) + bb.z);
-            o.w = fast_tanh(__uint_as_float(v[4 * q + 3]) + bb.w);
-            dst[q] = o;
+            // same tanh formulation as the tile-blocked (inference) store: train and eval give the same Q bits
+            const f2 t0 = fast_tanh2(add2(f2{__uint_as_float(v[4 * q + 0]), __uint_as_float(v[4 * q + 1])}, f2{bb.x, bb.y}));
+            const f2 t1 = fast_tanh2(add2(f2{__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])}, f2{bb.z, bb.w}));
+            dst[q] = make_float4(t0.x, t0.y, t1.x, t1.y);
           }
         }
       }
