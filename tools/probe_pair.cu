@@ -1,0 +1,312 @@
+// First-contact probe for the mechanisms of the CTA-pair phase-1 kernel (DESIGN.md "pair kernel"), one
+// 256-row super-tile, layer 1 only (H1acc = X . W1^T, 3xBF16 split):
+//
+//   * cluster of 2 CTAs, tcgen05.alloc/dealloc.cta_group::2, tcgen05.mma.cta_group::2 (M=256: 128 rows per CTA)
+//   * A operand from TENSOR MEMORY: X boxes [128 rows x 32 k] fp32 arrive by TMA (cp.async.bulk.tensor.2d,
+//     SWIZZLE_128B), converter warps (lane = row) split them into bf16 hi/lo and tcgen05.st them into 4 TMEM stages
+//   * B operand: each CTA holds HALF of the weight image (64 of the 128 output features) resident in shared memory
+//   * cross-CTA handshakes: remote mbarrier arrives (mapa) towards the leader, multicast tcgen05.commit back
+//
+// Prints the max error of H1acc against fp64 and exits non-zero on failure.
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/probe_pair tools/probe_pair.cu -lcuda
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+constexpr int D = 512, NQ = 128, ROWS = 256;
+constexpr int kBoxK = 32, kBoxes = D / kBoxK;           // 16 boxes of [128 rows x 32 floats] = 16 KB
+constexpr int kStageBytes = 128 * kBoxK * 4;            // 16 KB
+constexpr int kXStages = 3;
+constexpr int kWChunkBytes = 2 * 64 * 128;              // per 64-k chunk: hi tile [64 rows x 128 B] + lo tile = 16 KB
+constexpr int kWBytes = (D / 64) * kWChunkBytes;        // 128 KB per CTA
+constexpr int kGroups = 3;                               // converter groups == staging stages == TMEM operand stages
+constexpr int kThreads = 32 * 20;
+constexpr int kWarpProd = 0, kWarpMma = 1, kWarpAlloc = 2, kWarpConv0 = 4, kWarpEpi0 = 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t cta_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+template <bool CLUSTER>
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    if (CLUSTER)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    else
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spins > (1u << 24)) { printf("TIMEOUT bar=%u parity=%u block=%d thread=%d\n", bar, parity, blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar) {   // arrive on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+#define TMEM_ST16(taddr, v)                                                                                  \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),   \
+                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory")
+#define TMEM_LD16(taddr, v)                                                                                \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                   \
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                            \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),       \
+                 "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),   \
+                 "=r"(v[14]), "=r"(v[15])                                                                  \
+               : "r"(taddr) : "memory")
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N=128, M=256 (cta_group::2: 128 rows per CTA)
+constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+// K-major SWIZZLE_128B smem descriptor, SBO = 1024 B, version 1
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3ffffu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void mma2_ts(uint32_t d, uint32_t a_tmem, uint32_t blo, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %3, 0;\n\t"
+      "mov.b64 db, {%2, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %5, p;\n\t}"
+      ::"r"(d), "r"(a_tmem), "r"(blo), "r"(acc), "r"(kDescHi), "r"(kIdesc2) : "memory");
+}
+__host__ __device__ inline uint32_t swz_off(int row, int k) {   // (row, k) in a [rows x 64] bf16 SWIZZLE_128B tile
+  return static_cast<uint32_t>(row * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + ((k & 7) << 1));
+}
+
+struct Args {
+  const CUtensorMap* tmap;   // X [ROWS x D] fp32, box {32, 128}, SWIZZLE_128B (device copy)
+  const uint8_t* wimg;       // [2 ranks][D/64 chunks][hi 8 KB | lo 8 KB]
+  float* out;                // [ROWS x 128]
+  int mode;                  // bit0: leave out the lo products (debug)
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_probe2(const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bars[32];
+  __shared__ uint32_t s_tmem;
+  // group g (4 warps, one per TMEM lane quadrant) owns staging stage g and TMEM operand stage g and handles the boxes
+  // n = g, g+3, ...: every barrier has ONE waiting party that sees every phase in order (a shared 3-slot ring with 4
+  // groups would let a group wait for use u+1 of a slot before use u has completed -- parity aliasing)
+  enum { XS_FULL = 0, XS_EMPTY = XS_FULL + kGroups, XT_FULL = XS_EMPTY + kGroups, XT_EMPTY = XT_FULL + kGroups,
+         H1_FULL = XT_EMPTY + kGroups, W_BAR, W_READY, NBARS };
+  auto bar = [&](int i) { return smem_u32(&bars[i]); };
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cta_rank();
+  uint8_t* sW = smem;
+  uint8_t* sX = smem + kWBytes;
+  if (tid == 0) {
+    for (int s = 0; s < kXStages; ++s) { mbar_init(bar(XS_FULL + s), 1); mbar_init(bar(XS_EMPTY + s), 4); }
+    for (int s = 0; s < kGroups; ++s) { mbar_init(bar(XT_FULL + s), 8); mbar_init(bar(XT_EMPTY + s), 1); }
+    mbar_init(bar(H1_FULL), 1);
+    mbar_init(bar(W_BAR), 1);
+    mbar_init(bar(W_READY), 2);               // leader's copy is the one used: both CTAs report "weights resident"
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kWarpAlloc) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t tm_acc = tmem, tm_x = tmem + 384;
+
+  if (warp == kWarpProd) {
+    if (lane == 0) {
+      mbar_expect_tx(bar(W_BAR), kWBytes);
+      for (int c = 0; c < D / 64; ++c)
+        bulk_g2s(smem_u32(sW + c * kWChunkBytes), a.wimg + static_cast<size_t>(rank) * kWBytes + c * kWChunkBytes, kWChunkBytes, bar(W_BAR));
+      for (int n = 0; n < kBoxes; ++n) {
+        const int s = n % kGroups;
+        mbar_wait<false>(bar(XS_EMPTY + s), ((n / kGroups) & 1) ^ 1);
+        mbar_expect_tx(bar(XS_FULL + s), kStageBytes);
+        tma_load_2d(smem_u32(sX + s * kStageBytes), a.tmap, n * kBoxK, static_cast<int>(rank) * 128, bar(XS_FULL + s));
+      }
+      // weights of this CTA resident -> tell the leader (async-proxy writes are visible after the mbarrier wait)
+      mbar_wait<false>(bar(W_BAR), 0);
+      if (rank == 0) mbar_arrive(bar(W_READY)); else mbar_arrive_cluster(bar(W_READY), 0);
+    }
+  } else if (warp >= kWarpConv0 && warp < kWarpConv0 + 4 * kGroups) {
+    const int cw = warp - kWarpConv0, q = cw & 3, sub = cw >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+    for (int n = sub; n < kBoxes; n += kGroups) {
+      const int s = sub, m = n / kGroups;
+      mbar_wait<false>(bar(XS_FULL + s), m & 1);
+      const uint32_t rowb = smem_u32(sX + s * kStageBytes) + r * 128;
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 x = lds128(rowb + (((j ^ (r & 7)) & 7) << 4));
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
+        const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - __uint_as_float(u01 << 16), x.y - __uint_as_float(u01 & 0xffff0000u));
+        const __nv_bfloat162 l23 = __floats2bfloat162_rn(x.z - __uint_as_float(u23 << 16), x.w - __uint_as_float(u23 & 0xffff0000u));
+        hi[2 * j] = u01; hi[2 * j + 1] = u23;
+        lo[2 * j] = *reinterpret_cast<const uint32_t*>(&l01); lo[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(XS_EMPTY + s));
+      mbar_wait<false>(bar(XT_EMPTY + sub), (m & 1) ^ 1);
+      tc_fence_after();
+      TMEM_ST16(tm_x + lane_sel + sub * 32, hi);
+      TMEM_ST16(tm_x + lane_sel + sub * 32 + 16, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(bar(XT_FULL + sub)); else mbar_arrive_cluster(bar(XT_FULL + sub), 0);
+      }
+    }
+  } else if (warp == kWarpMma) {
+    if (rank == 0 && lane == 0) {
+      mbar_wait<true>(bar(W_READY), 0);
+      tc_fence_after();
+      const uint32_t wbase = desc_lo(smem_u32(sW));
+      for (int n = 0; n < kBoxes; ++n) {
+        const int sub = n % kGroups;
+        mbar_wait<true>(bar(XT_FULL + sub), (n / kGroups) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const int kabs = n * kBoxK + ks * 16, kc = kabs >> 6, koff = kabs & 63;
+          const uint32_t bhi = wbase + ((kc * kWChunkBytes + koff * 2) >> 4);      // hi tile of chunk kc, +32 B per K step
+          const uint32_t blo = bhi + ((64 * 128) >> 4);                            // lo tile 8 KB further
+          const uint32_t ahi = tm_x + sub * 32 + ks * 8, alo = ahi + 16;
+          mma2_ts(tm_acc, ahi, bhi, (n | ks) != 0);
+          if (!(a.mode & 1)) {
+            mma2_ts(tm_acc, alo, bhi, 1);
+            mma2_ts(tm_acc, ahi, blo, 1);
+          }
+        }
+        tc_commit_mc(bar(XT_EMPTY + sub));
+      }
+      tc_commit_mc(bar(H1_FULL));
+    }
+  } else if (warp >= kWarpEpi0) {
+    const int q = warp & 3;
+    const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+    mbar_wait<false>(bar(H1_FULL), 0);
+    tc_fence_after();
+    float* dst = a.out + (static_cast<size_t>(rank) * 128 + q * 32 + lane) * NQ;
+    for (int c0 = 0; c0 < NQ; c0 += 16) {
+      uint32_t v[16];
+      TMEM_LD16(tm_acc + lane_sel + c0, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dst[c0 + i] = __uint_as_float(v[i]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == kWarpAlloc) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+static float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+int main(int argc, char** argv) {
+  const int mode = argc > 1 ? atoi(argv[1]) : 0;
+  std::vector<float> X(ROWS * D), W(NQ * D);
+  uint32_t st = 12345;
+  auto rnd = [&]() { st = st * 1664525u + 1013904223u; return (st >> 8) * (1.f / 16777216.f); };
+  for (auto& v : X) v = rnd();
+  for (auto& v : W) v = (rnd() - 0.5f) * 0.2f;
+  // weight image: [rank][chunk][hi | lo], rows = local output feature 0..63
+  std::vector<uint8_t> img(2 * kWBytes, 0);
+  for (int n = 0; n < NQ; ++n)
+    for (int k = 0; k < D; ++k) {
+      const float w = W[n * D + k];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(w), lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+      uint8_t* chunk = img.data() + static_cast<size_t>(n / 64) * kWBytes + (k / 64) * kWChunkBytes;
+      const uint32_t off = swz_off(n % 64, k % 64);
+      *reinterpret_cast<__nv_bfloat16*>(chunk + off) = hi;
+      *reinterpret_cast<__nv_bfloat16*>(chunk + 64 * 128 + off) = lo;
+    }
+  float *dX, *dOut; uint8_t* dImg; CUtensorMap* dMap;
+  cudaMalloc(&dX, X.size() * 4); cudaMalloc(&dOut, ROWS * NQ * 4); cudaMalloc(&dImg, img.size()); cudaMalloc(&dMap, sizeof(CUtensorMap));
+  cudaMemcpy(dX, X.data(), X.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dImg, img.data(), img.size(), cudaMemcpyHostToDevice);
+  cudaMemset(dOut, 0xff, ROWS * NQ * 4);
+  CUtensorMap tm;
+  const cuuint64_t gdim[2] = {D, ROWS};
+  const cuuint64_t gstr[1] = {D * sizeof(float)};
+  const cuuint32_t box[2] = {kBoxK, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult cr = cuTensorMapEncodeTiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dX, gdim, gstr, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled failed: %d\n", (int)cr); return 2; }
+  cudaMemcpy(dMap, &tm, sizeof(tm), cudaMemcpyHostToDevice);
+  const size_t smem = kWBytes + kXStages * kStageBytes + 1024;
+  cudaFuncSetAttribute(k_probe2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  Args a{dMap, dImg, dOut, mode};
+  k_probe2<<<2, kThreads, smem>>>(a);
+  cudaError_t e = cudaDeviceSynchronize();
+  printf("kernel: %s\n", cudaGetErrorString(e));
+  if (e != cudaSuccess) return 3;
+  std::vector<float> out(ROWS * NQ);
+  cudaMemcpy(out.data(), dOut, out.size() * 4, cudaMemcpyDeviceToHost);
+  double max_err = 0, max_ref = 0, max_err_hi = 0;
+  double q_err[2][2] = {{0, 0}, {0, 0}};   // [row half = CTA][column half = weight half]
+  for (int r = 0; r < ROWS; ++r)
+    for (int n = 0; n < NQ; ++n) {
+      double ref = 0, ref_hi = 0;
+      for (int k = 0; k < D; ++k) {
+        ref += (double)X[r * D + k] * W[n * D + k];
+        ref_hi += (double)bf16_round(X[r * D + k]) * bf16_round(W[n * D + k]);
+      }
+      max_ref = fmax(max_ref, fabs(ref));
+      max_err = fmax(max_err, fabs(out[r * NQ + n] - ref));
+      q_err[r / 128][n / 64] = fmax(q_err[r / 128][n / 64], fabs(out[r * NQ + n] - ref));
+      max_err_hi = fmax(max_err_hi, fabs(out[r * NQ + n] - ref_hi));
+    }
+  printf("mode=%d  max|ref|=%.4f  max err vs fp64 = %.3e  (vs hi*hi only: %.3e)\n", mode, max_ref, max_err, max_err_hi);
+  printf("err by quadrant: rows0-127/cols0-63 %.2e  rows0-127/cols64-127 %.2e  rows128-255/cols0-63 %.2e  rows128-255/cols64-127 %.2e\n",
+         q_err[0][0], q_err[0][1], q_err[1][0], q_err[1][1]);
+  printf("sample out[0][0..3] = %g %g %g %g ; out[200][5] = %g\n", out[0], out[1], out[2], out[3], out[200 * NQ + 5]);
+  const bool ok = mode == 0 ? max_err < 2e-5 * fmax(max_ref, 1.0) : max_err_hi < 2e-5 * fmax(max_ref, 1.0);
+  printf(ok ? "PROBE OK\n" : "PROBE FAILED\n");
+  return ok ? 0 : 1;
+}
