@@ -15,6 +15,7 @@
 #include "bwd_kernels.cuh"
 #include "fwd_sm100.cuh"
 #include "fwd_batched.cuh"
+#include "fwd_pair.cuh"
 
 namespace dsmil {
 
@@ -177,6 +178,14 @@ static bool use_sm100(const dsmil_params_t* p) {
   return !disabled && sm100::qmlp_supported(p);
 }
 
+static bool use_pair(const dsmil_params_t* p) {
+  // CTA-pair phase 1 (fwd_pair.cuh): parity-green, but not yet faster than k_qmlp_sm100 (profiles/r2_bench_history.md),
+  // so it is opt-in: DSMIL_B200_PAIR=1
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("DSMIL_B200_PAIR"); enabled = (e && e[0] == '1') ? 1 : 0; }
+  return enabled && use_sm100(p) && pair::pair_supported(p);
+}
+
 static int phase1_impl(const dsmil_params_t* p, const float* X, const float* xv, const float* classes_in,
                        int64_t N, int64_t row_offset, float* classes, float* Q, float* H1, float* V,
                        float* cand, unsigned long long* keys, uint8_t* wimg, cudaStream_t st) {
@@ -329,6 +338,7 @@ static int forward_impl(const dsmil_params_t* p, const float* X, const float* xv
 // ---- batched forward: a stream of bags in a handful of launches (tensor-core path only) -----------
 struct BagsWs {
   sm100::BagDev* table;
+  CUtensorMap* tmaps;       // one per bag (pair kernel: X of the bag as a 2-D TMA tensor)
   unsigned long long* keys;
   float* Q;
   uint8_t* wimg;
@@ -348,6 +358,7 @@ static BagsWs carve_bags(const dsmil_params_t* p, const int64_t* Ns, int nb, boo
   int64_t total = 0, nrec = 0;
   for (int b = 0; b < nb; ++b) { total += Ns[b]; nrec += recs_for_bag(Ns[b]); }
   w.table = c.take<sm100::BagDev>(nb);
+  w.tmaps = c.take<CUtensorMap>(nb);
   // keys and the finalize arrival counters are zeroed together (one memset): keep them adjacent
   w.keys = c.take<unsigned long long>(static_cast<size_t>(nb) * (kMaxC + 1));
   w.counters = reinterpret_cast<unsigned int*>(w.keys ? w.keys + static_cast<size_t>(nb) * kMaxC : nullptr);
@@ -404,12 +415,32 @@ static int forward_bags_impl(const dsmil_params_t* p, const float* const* Xs, co
   DSMIL_CUDA_OK(cudaMemsetAsync(w.keys, 0, sizeof(unsigned long long) * (kMaxC + 1) * nb, st));
   uint8_t* img = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(w.wimg) + 1023) & ~uintptr_t(1023));
   int rc;
-  if ((rc = sm100::launch_prep_wimg(p, img, st))) return rc;
+  // inference (Q stays in the tile-blocked workspace) on D <= 512: the CTA-pair kernel (fwd_pair.cuh)
+  const bool pair_path = save_Q == nullptr && save_H1 == nullptr && use_pair(p);
+  if (pair_path) {
+    std::vector<CUtensorMap> maps(nb);
+    for (int b = 0; b < nb; ++b)
+      if ((rc = pair::encode_bag_tmap(&maps[b], Xs[b], Ns[b], D))) return rc;
+    DSMIL_CUDA_OK(cudaMemcpyAsync(w.tmaps, maps.data(), sizeof(CUtensorMap) * nb, cudaMemcpyHostToDevice, st));
+    if ((rc = pair::launch_prep_wimg_pair(p, img, st))) return rc;
+  } else {
+    if ((rc = sm100::launch_prep_wimg(p, img, st))) return rc;
+  }
   float* Q = save_Q ? save_Q : w.Q;
   if (classes_in) {   // bag form: arg-max of the given scores (single bag only)
     const int grid = static_cast<int>(std::min<int64_t>(ceil_div(Ns[0], 256), 296));
     k_argmax<<<grid, 256, 0, st>>>(classes_in, Ns[0], C, w.keys);
     DSMIL_LAUNCH_OK("k_argmax");
+  }
+  if (pair_path) {
+    if ((rc = pair::launch_fwd_pair(p, w.table, w.tmaps, nb, tile, classes_in ? nullptr : classes, w.keys, Q, img,
+                                    num_sms(), st)))
+      return rc;
+    sm100::AttendArgs aa{w.table, 0, nb, 0, D, C, Q, 1, w.keys, A, w.recs, nullptr};
+    if ((rc = sm100::launch_attend_b(aa, rec, st))) return rc;
+    sm100::FinalizeArgs fa{w.table, 0, D, C, w.recs, w.keys, p->Wf, p->bf, A, B, pred,
+                           reinterpret_cast<long long*>(crit), w.pred_part, w.counters, nullptr, 0, 0};
+    return sm100::launch_finalize_b(fa, nb, st);
   }
   // sub-batches sized so that a sub-batch's features (+Q) are still in L2 when the attend pass re-reads them
   const size_t budget = l2_budget_bytes();

@@ -56,3 +56,12 @@ def pred_tolerance_ok(pred, ref_pred, p: orc.Params, B_ref, tol):
     terms = np.abs(p.Wf.reshape(p.C, -1)).astype(np.float64) @ np.abs(np.asarray(B_ref, np.float64).reshape(-1))
     err = np.abs(np.asarray(pred, np.float64).reshape(-1) - np.asarray(ref_pred, np.float64).reshape(-1))
     return bool(np.all(err <= tol * np.maximum(np.abs(np.asarray(ref_pred, np.float64).reshape(-1)), terms))), err
+
+
+def scores_close(a, b, tol=2e-6):
+    """Instance scores from two DIFFERENT kernels (pair kernel / k_qmlp_sm100 / k_scores: each sums the D products of a
+    row in its own fixed order): equal to the tolerance every path is held to against the reference (2e-6 of the
+    largest score); the arg-max they select is asserted bit-exact separately."""
+    a = a.detach().float().cpu().numpy().astype(np.float64)
+    b = b.detach().float().cpu().numpy().astype(np.float64)
+    return a.shape == b.shape and float(np.max(np.abs(a - b))) <= tol * max(float(np.max(np.abs(b))), 1e-30)

@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from conftest import golden_names, load_golden, rel_to_max
-from helpers import build_net, caller_loss, grad_name, pred_tolerance_ok
+from helpers import scores_close, build_net, caller_loss, grad_name, pred_tolerance_ok
 from oracle import dsmil_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -129,7 +129,9 @@ def test_split_call_forms_compose_to_fused():
         feats, c2 = net.i_classifier(x)
         p2, A2, B2 = net.b_classifier(feats, c2)
     assert feats is x
-    assert torch.equal(c1, c2) and torch.equal(A1, A2) and torch.equal(B1, B2) and torch.equal(p1, p2)
+    # scores: fused kernel vs k_scores (different fixed summation orders); everything downstream of the SAME arg-max is
+    # computed by the same kernels in both forms -> bit-identical
+    assert scores_close(c1, c2) and torch.equal(A1, A2) and torch.equal(B1, B2) and torch.equal(p1, p2)
 
 
 def test_iclassifier_backbone_path_and_rekeyed_weights():
@@ -148,7 +150,7 @@ def test_iclassifier_backbone_path_and_rekeyed_weights():
         feats, c = net2.i_classifier(x.view(-1, 8, 8, 8))
     for u, v in zip(a, b):
         assert torch.equal(u, v)
-    assert feats.shape == (X.shape[0], 512) and torch.equal(c, a[0])
+    assert feats.shape == (X.shape[0], 512) and scores_close(c, a[0])
 
 
 def test_ties_and_permutation_properties():

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from conftest import load_golden, rel_to_max
-from helpers import build_net
+from helpers import scores_close, build_net
 from oracle import dsmil_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -31,7 +31,7 @@ def test_virtual_shards_match_single_device_and_oracle(name, G):
     ops = CudaShardOps(milnet_params(net))
     c2, p2, A2, B2, crit = virtual_sharded_forward(ops, x, G)
     assert np.array_equal(_np(crit), g["idx"])
-    assert torch.equal(c1, c2)
+    assert scores_close(c1, c2)
     assert rel_to_max(_np(A2), _np(A1)) < 2e-6 and rel_to_max(_np(B2), _np(B1)) < 2e-6
     assert rel_to_max(_np(p2), _np(p1)) < 1e-5
     t = orc.forward(X, p)
@@ -107,7 +107,7 @@ def test_batched_sharded_phases_single_rank_and_virtual():
     recs = b1.phase2(cand.view(-1), 1)
     out = b1.phase3(recs.view(-1), 1)
     for o, r in zip(out, ref):
-        assert torch.equal(o[0], r[0])
+        assert scores_close(o[0], r[0])
         assert rel_to_max(_np(o[2]), _np(r[2])) < 2e-6 and rel_to_max(_np(o[3]), _np(r[3])) < 2e-6
         assert rel_to_max(_np(o[1]), _np(r[1])) < 1e-5
     # (b) two logical ranks

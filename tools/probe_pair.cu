@@ -49,7 +49,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 template <bool CLUSTER>
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int site = 0) {
   uint32_t done = 0;
   for (uint32_t spins = 0; !done; ++spins) {
     if (CLUSTER)
@@ -58,7 +58,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     else
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                    : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (spins > (1u << 24)) { printf("TIMEOUT bar=%u parity=%u block=%d thread=%d\n", bar, parity, blockIdx.x, threadIdx.x); __trap(); }
+    if (spins > (1u << 22)) {
+      if ((threadIdx.x & 31) == 0 || site >= 100)
+        printf("TIMEOUT site=%d bar=0x%x parity=%u block=%d warp=%d\n", site, bar, parity, blockIdx.x, threadIdx.x >> 5);
+      __nanosleep(2000000);     // let the other stuck roles print before the trap kills the context
+      __trap();
+    }
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -154,15 +159,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_probe
       mbar_expect_tx(bar(W_BAR), kWBytes);
       for (int c = 0; c < D / 64; ++c)
         bulk_g2s(smem_u32(sW + c * kWChunkBytes), a.wimg + static_cast<size_t>(rank) * kWBytes + c * kWChunkBytes, kWChunkBytes, bar(W_BAR));
+      // weights of this CTA resident -> tell the leader BEFORE the box loop (the loop only ends once the MMAs, which
+      // wait for W_READY, have released the slots)
+      mbar_wait<false>(bar(W_BAR), 0, 190);
+      if (rank == 0) mbar_arrive(bar(W_READY)); else mbar_arrive_cluster(bar(W_READY), 0);
       for (int n = 0; n < kBoxes; ++n) {
         const int s = n % kGroups;
-        mbar_wait<false>(bar(XS_EMPTY + s), ((n / kGroups) & 1) ^ 1);
+        mbar_wait<false>(bar(XS_EMPTY + s), ((n / kGroups) & 1) ^ 1, 100 + n);
         mbar_expect_tx(bar(XS_FULL + s), kStageBytes);
         tma_load_2d(smem_u32(sX + s * kStageBytes), a.tmap, n * kBoxK, static_cast<int>(rank) * 128, bar(XS_FULL + s));
       }
-      // weights of this CTA resident -> tell the leader (async-proxy writes are visible after the mbarrier wait)
-      mbar_wait<false>(bar(W_BAR), 0);
-      if (rank == 0) mbar_arrive(bar(W_READY)); else mbar_arrive_cluster(bar(W_READY), 0);
     }
   } else if (warp >= kWarpConv0 && warp < kWarpConv0 + 4 * kGroups) {
     const int cw = warp - kWarpConv0, q = cw & 3, sub = cw >> 2;
@@ -170,7 +176,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_probe
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
     for (int n = sub; n < kBoxes; n += kGroups) {
       const int s = sub, m = n / kGroups;
-      mbar_wait<false>(bar(XS_FULL + s), m & 1);
+      mbar_wait<false>(bar(XS_FULL + s), m & 1, 1);
       const uint32_t rowb = smem_u32(sX + s * kStageBytes) + r * 128;
       uint32_t hi[16], lo[16];
 #pragma unroll
@@ -185,7 +191,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_probe
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(XS_EMPTY + s));
-      mbar_wait<false>(bar(XT_EMPTY + sub), (m & 1) ^ 1);
+      mbar_wait<false>(bar(XT_EMPTY + sub), (m & 1) ^ 1, 2);
       tc_fence_after();
       TMEM_ST16(tm_x + lane_sel + sub * 32, hi);
       TMEM_ST16(tm_x + lane_sel + sub * 32 + 16, lo);
@@ -198,12 +204,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_probe
     }
   } else if (warp == kWarpMma) {
     if (rank == 0 && lane == 0) {
-      mbar_wait<true>(bar(W_READY), 0);
+      mbar_wait<true>(bar(W_READY), 0, 200);
       tc_fence_after();
       const uint32_t wbase = desc_lo(smem_u32(sW));
       for (int n = 0; n < kBoxes; ++n) {
         const int sub = n % kGroups;
-        mbar_wait<true>(bar(XT_FULL + sub), (n / kGroups) & 1);
+        mbar_wait<true>(bar(XT_FULL + sub), (n / kGroups) & 1, 201 + n);
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
@@ -224,7 +230,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_probe
   } else if (warp >= kWarpEpi0) {
     const int q = warp & 3;
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
-    mbar_wait<false>(bar(H1_FULL), 0);
+    mbar_wait<false>(bar(H1_FULL), 0, 3);
     tc_fence_after();
     float* dst = a.out + (static_cast<size_t>(rank) * 128 + q * 32 + lane) * NQ;
     for (int c0 = 0; c0 < NQ; c0 += 16) {
@@ -244,10 +250,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_probe
   }
 }
 
+// ---- isolated TMA tests: one box [128 rows x 32 floats] per CTA -> staging -> raw copy to global ----------------
+struct TmaArgs { const CUtensorMap* tmap; float* out; };
+template <int CLUSTER, int PARAM>
+__device__ __forceinline__ void tma_test_body(const CUtensorMap* tm, float* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t fullbar;
+  const uint32_t rank = CLUSTER ? cta_rank() : blockIdx.x;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&fullbar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (CLUSTER) cluster_sync();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(smem_u32(&fullbar), kStageBytes);
+    tma_load_2d(smem_u32(smem), tm, 64, static_cast<int>(rank) * 128, smem_u32(&fullbar));   // box kb = 2
+  }
+  mbar_wait<false>(smem_u32(&fullbar), 0, 300 + CLUSTER * 10 + PARAM);
+  const float* s = reinterpret_cast<const float*>(smem);
+  for (int i = threadIdx.x; i < 128 * 32; i += blockDim.x) out[static_cast<size_t>(rank) * 4096 + i] = s[i];
+  __syncthreads();
+  if (CLUSTER) cluster_sync();
+}
+__global__ void __launch_bounds__(128) k_tma_param(const __grid_constant__ CUtensorMap tm, float* out) { tma_test_body<0, 1>(&tm, out); }
+__global__ void __launch_bounds__(128) k_tma_global(const CUtensorMap* tm, float* out) { tma_test_body<0, 0>(tm, out); }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) k_tma_cluster_param(const __grid_constant__ CUtensorMap tm, float* out) { tma_test_body<1, 1>(&tm, out); }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) k_tma_cluster_global(const CUtensorMap* tm, float* out) { tma_test_body<1, 0>(tm, out); }
+
 static float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 int main(int argc, char** argv) {
-  const int mode = argc > 1 ? atoi(argv[1]) : 0;
+  const int mode = argc > 1 ? atoi(argv[1]) : 0;       // 0/1: full probe; 10..13: isolated TMA tests
   std::vector<float> X(ROWS * D), W(NQ * D);
   uint32_t st = 12345;
   auto rnd = [&]() { st = st * 1664525u + 1013904223u; return (st >> 8) * (1.f / 16777216.f); };
@@ -279,6 +314,30 @@ int main(int argc, char** argv) {
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled failed: %d\n", (int)cr); return 2; }
   cudaMemcpy(dMap, &tm, sizeof(tm), cudaMemcpyHostToDevice);
+  if (mode >= 10) {
+    float* dT; cudaMalloc(&dT, 2 * 4096 * 4); cudaMemset(dT, 0, 2 * 4096 * 4);
+    const size_t sm = kStageBytes + 1024;
+    if (mode == 10) k_tma_param<<<2, 128, sm>>>(tm, dT);
+    if (mode == 11) k_tma_global<<<2, 128, sm>>>(dMap, dT);
+    if (mode == 12) k_tma_cluster_param<<<2, 128, sm>>>(tm, dT);
+    if (mode == 13) k_tma_cluster_global<<<2, 128, sm>>>(dMap, dT);
+    cudaError_t e = cudaDeviceSynchronize();
+    printf("tma test %d: %s\n", mode, cudaGetErrorString(e));
+    if (e != cudaSuccess) return 3;
+    std::vector<float> t(2 * 4096);
+    cudaMemcpy(t.data(), dT, t.size() * 4, cudaMemcpyDeviceToHost);
+    // expected staging layout: row r at r*128 B, 16-byte unit j (floats 4j..4j+3 of the box) at unit j ^ (r & 7)
+    int bad = 0;
+    for (int c = 0; c < 2; ++c)
+      for (int r = 0; r < 128; ++r)
+        for (int k = 0; k < 32; ++k) {
+          const float want = X[(c * 128 + r) * D + 64 + k];
+          const float got = t[c * 4096 + r * 32 + (((k >> 2) ^ (r & 7)) << 2) + (k & 3)];
+          if (want != got && bad++ < 5) printf("  mismatch cta %d row %d k %d: want %g got %g\n", c, r, k, want, got);
+        }
+    printf(bad ? "TMA TEST FAILED (%d mismatches)\n" : "TMA TEST OK\n", bad);
+    return bad ? 1 : 0;
+  }
   const size_t smem = kWBytes + kXStages * kStageBytes + 1024;
   cudaFuncSetAttribute(k_probe2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   Args a{dMap, dImg, dOut, mode};
