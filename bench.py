@@ -360,8 +360,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     from dsmil_wsi_b200 import _lib
     from dsmil_wsi_b200.pipeline import HostBagPipeline
-    from dsmil_wsi_b200.sharded import (CudaShardBagOps, CudaShardOps, milnet_params, sharded_forward_bags,
-                                        sharded_forward_bags_batched)
+    from dsmil_wsi_b200.sharded import (CudaShardBagOps, CudaShardOps, ShardedBagsGraph, milnet_params,
+                                        sharded_forward_bags, sharded_forward_bags_batched)
     lib = _lib.load()
 
     p = make_params()
@@ -382,10 +382,24 @@ def run_ours(args):
             return sharded_forward_bags_batched(bops, xs, offsets)
         return sharded_forward_bags(ops, xs, offsets)
 
+    # the serving-loop form of the sharded step: one CUDA graph (3 library calls + 2 NCCL all-gathers) per step
+    plan = None
+    graph_note = "eager (host-launched)"
+    if world > 1 and bops is not None and not args.no_graph:
+        try:
+            with torch.no_grad():
+                plan = ShardedBagsGraph(bops, bags, offsets)
+            graph_note = "CUDA graph replay (dsmil_wsi_b200.sharded.ShardedBagsGraph)"
+        except Exception as e:                     # same code on every rank: the decision is collective
+            plan = None
+            graph_note = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+
     def step():
         with torch.no_grad():
             if world == 1:
                 return net.forward_bags(bags)
+            if plan is not None:
+                return plan.replay()
             return sharded_step(bags)
 
     def barrier():
@@ -436,8 +450,9 @@ def run_ours(args):
     # ---- roofline: whole forward step (headline) + the dominant kernel, timed live with CUDA events ----
     hbm_peak, tf_peak, peak_src = load_peaks()
     lib.dsmil_profile_enable(1)
-    for _ in range(2):
-        step()
+    for _ in range(2):                             # host-launched here: graph replays carry no per-kernel event pairs
+        with torch.no_grad():
+            net.forward_bags(bags) if world == 1 else sharded_step(bags)
     torch.cuda.synchronize()
     ms_tag = (ctypes.c_double * 8)()
     n_tag = (ctypes.c_uint64 * 8)()
@@ -529,10 +544,20 @@ def run_ours(args):
             del full
         goff = [lo] * nbg
 
+        gplan = None
+        if plan is not None:                       # same decision on every rank
+            try:
+                with torch.no_grad():
+                    gplan = ShardedBagsGraph(CudaShardBagOps(milnet_params(net)), giant, goff)
+            except Exception:
+                gplan = None
+
         def gstep():
             with torch.no_grad():
                 if world == 1:
                     return net.forward_bags(giant)
+                if gplan is not None:
+                    return gplan.replay()
                 if bops is not None:
                     return sharded_forward_bags_batched(bops, giant, goff)
                 return sharded_forward_bags(ops, giant, goff)
@@ -554,7 +579,8 @@ def run_ours(args):
         strong = {"workload": f"{nbg} giant bags x N={NG} x D={D}, C={C}, rows sharded over {world} GPU(s) "
                               f"({hi - lo} rows/rank/bag); {nbg * NG * D * 4 / 1e6:.0f} MB of features in total (> L2)",
                   "scaling": "strong", "value": nbg * NG / (gms / 1e3), "unit": "patches/s", "ms_per_step": gms,
-                  "n_gpus": world, "hbm_frac_per_gpu": galg / world / (gms / 1e3) / 1e9 / hbm_peak}
+                  "n_gpus": world, "hbm_frac_per_gpu": galg / world / (gms / 1e3) / 1e9 / hbm_peak,
+                  "step_launch": "CUDA graph replay" if gplan is not None else "eager"}
         del giant
 
     # ---- multi-rank parity check (outside every timed region): one sharded forward against the CPU oracle ------
@@ -596,6 +622,7 @@ def run_ours(args):
                                       f"(U[0,1)), C={C}, nonlinear q, identity v; MILNet forward; "
                                       f"{'one GPU' if world == 1 else f'rows sharded over {world} GPUs ({NBAG} rows/rank/bag)'}",
                           "bags_per_step": nb, "rows_per_rank_per_bag": NBAG, "parallelism": f"row-shard x{world}",
+                          "step_launch": graph_note if world > 1 else "eager: one forward_bags call per step",
                           "l2_policy": f"inputs larger than L2: {nb} bags x {NBAG * D * 4 / 1e6:.1f} MB per rank cycled",
                           "forward_path": int(lib.dsmil_forward_path(ctypes.byref(_lib.DsmilParams(D, C, 1, 0)), NBAG))},
                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches * world,
@@ -614,6 +641,7 @@ def main():
     ap.add_argument("--bags", type=int, default=16, help="bags per step (16 x 20.5 MB > L2)")
     ap.add_argument("--ref-bags", type=int, default=16)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-graph", action="store_true", help="multi-GPU: host-launched step instead of the CUDA-graph replay")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra workloads (eager-GPU baseline, N=8192, "
                     "N=15000 training step, N=100k strong scaling, multi-rank parity check)")
     ap.add_argument("--giant-bags", type=int, default=4, help="N=100 000 bags per step of the strong-scaling workload")

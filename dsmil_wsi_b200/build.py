@@ -46,7 +46,6 @@ def build_library(force=False, verbose=False):
     cmd = [_nvcc(), "-O3", "-std=c++17", "-lineinfo", *ARCH, "-shared", "-Xcompiler", "-fPIC,-O3",
            "-Xptxas", "-v" if verbose else "-O3",
            "-I", os.path.join(HERE, "..", "include"), "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    cmd += ["-lcuda"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

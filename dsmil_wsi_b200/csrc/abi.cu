@@ -178,6 +178,14 @@ static bool use_sm100(const dsmil_params_t* p) {
   return !disabled && sm100::qmlp_supported(p);
 }
 
+// Under stream capture (CUDA-graph serving loops) the pageable host->device copies of the bag table cannot be
+// recorded; the captured call then reuses the table that the preceding EAGER call with the same arguments wrote into
+// the same workspace (dsmil_wsi_b200.sharded.ShardedBagsGraph does exactly that: warm-up run, then capture).
+static bool stream_is_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+}
+
 static bool use_pair(const dsmil_params_t* p) {
   // CTA-pair phase 1 (fwd_pair.cuh): parity-green, but not yet faster than k_qmlp_sm100 (profiles/r2_bench_history.md),
   // so it is opt-in: DSMIL_B200_PAIR=1
@@ -599,6 +607,13 @@ int dsmil_forward_bags(const dsmil_params_t* p, const float* const* Xs, const in
   if (rc) return rc;
   DSMIL_REQUIRE(Xs && Ns && nb >= 1 && classes && pred && A && B, "NULL pointer or nb < 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {   // one contract for both routes below: the size dsmil_forward_bags_workspace_bytes reports
+    const size_t need = dsmil_forward_bags_workspace_bytes(p, Ns, nb);
+    if (!workspace || workspace_bytes < need) {
+      set_error("workspace too small: need %zu bytes, got %zu", need, workspace ? workspace_bytes : size_t(0));
+      return DSMIL_ERR_WORKSPACE;
+    }
+  }
   bool aligned = true;
   for (int b = 0; b < nb; ++b) aligned = aligned && Xs[b] && (reinterpret_cast<uintptr_t>(Xs[b]) & 15) == 0 && Ns[b] >= 1;
   if (use_sm100(p) && sm100::batched_supported(p) && aligned)
@@ -977,8 +992,10 @@ int dsmil_shard_bags_phase1(const dsmil_params_t* p, const float* const* Xs, con
   std::vector<sm100::BagDev> tbl;
   int tiles = 0, recs = 0;
   if ((rc = build_table(Xs, Ns, nb, tbl, &tiles, &recs))) return rc;
-  DSMIL_CUDA_OK(cudaMemcpyAsync(w.base.table, tbl.data(), sizeof(sm100::BagDev) * nb, cudaMemcpyHostToDevice, st));
-  DSMIL_CUDA_OK(cudaMemcpyAsync(w.row_offsets, row_offsets, sizeof(long long) * nb, cudaMemcpyHostToDevice, st));
+  if (!stream_is_capturing(st)) {
+    DSMIL_CUDA_OK(cudaMemcpyAsync(w.base.table, tbl.data(), sizeof(sm100::BagDev) * nb, cudaMemcpyHostToDevice, st));
+    DSMIL_CUDA_OK(cudaMemcpyAsync(w.row_offsets, row_offsets, sizeof(long long) * nb, cudaMemcpyHostToDevice, st));
+  }
   DSMIL_CUDA_OK(cudaMemsetAsync(w.base.keys, 0, sizeof(unsigned long long) * (kMaxC + 1) * nb, st));
   uint8_t* img = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(w.base.wimg) + 1023) & ~uintptr_t(1023));
   if ((rc = sm100::launch_prep_wimg(p, img, st))) return rc;

@@ -554,9 +554,25 @@ inline int encode_bag_tmap(CUtensorMap* tm, const float* X, long long N, int D) 
   const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(D) * sizeof(float)};
   const cuuint32_t box[2] = {kBoxK, kTileM};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), gdim, gstr, box,
-                                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  // resolved through the runtime (no link-time dependency on libcuda: the library must load on a machine without a
+  // driver, where only the host-side logic is exercised)
+  typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiled encode = nullptr;
+  if (encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess || fn == nullptr) {
+      set_error("cuTensorMapEncodeTiled is not available from the installed driver");
+      return DSMIL_ERR_CUDA;
+    }
+    encode = reinterpret_cast<EncodeTiled>(fn);
+  }
+  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) for a [%lld, %d] bag", static_cast<int>(r), N, D);
     return DSMIL_ERR_CUDA;

@@ -196,8 +196,11 @@ class CudaShardBagOps:
         self.c_X = (C.c_void_p * self.nb)(*[x.data_ptr() for x in self.xs])
         self.c_off = (C.c_int64 * self.nb)(*[int(o) for o in row_offsets])
         self.total = sum(self.Ns)
-        with torch.cuda.device(self.device):
-            self.ws = Fn._workspace(self.lib.dsmil_shard_bags_workspace_bytes(P.ref, self.c_N, self.nb), self.device)
+        key = (tuple(self.Ns), tuple(x.data_ptr() for x in self.xs), tuple(int(o) for o in row_offsets))
+        if getattr(self, "_ws_key", None) != key:       # same step again (serving loop / graph capture): keep the workspace
+            with torch.cuda.device(self.device):
+                self.ws = Fn._workspace(self.lib.dsmil_shard_bags_workspace_bytes(P.ref, self.c_N, self.nb), self.device)
+            self._ws_key = key
         self.cand_f = int(self.lib.dsmil_cand_floats(P.C))
         self.rec_f = int(self.lib.dsmil_rec_floats(P.C, P.D))
 
@@ -249,6 +252,33 @@ def sharded_forward_bags_batched(bops: "CudaShardBagOps", X_locals, row_offsets,
     recs = bops.phase2(cands_all, G)
     recs_all, G = _all_gather(recs.view(-1), group)         # exchange 2: [G][nb][rec]
     return bops.phase3(recs_all, G)
+
+
+class ShardedBagsGraph:
+    """Fixed-shape serving loop: the whole row-sharded step -- three library calls and the two NCCL all-gathers -- is
+    captured ONCE in a CUDA graph and replayed, so a step costs one graph launch instead of ~12 host-driven launches
+    (the sharded step is latency-, not bandwidth-bound: a few KB cross NVLink).  The bags' storage and shapes must
+    stay the same between replays (write new features INTO the same tensors); every rank must build and replay the
+    graph collectively."""
+
+    def __init__(self, bops: "CudaShardBagOps", X_locals, row_offsets, group=None, warmup: int = 3):
+        self.bops, self.xs, self.offs, self.group = bops, list(X_locals), list(row_offsets), group
+        side = torch.cuda.Stream(device=bops.device)
+        side.wait_stream(torch.cuda.current_stream(bops.device))
+        with torch.cuda.stream(side):               # eager warm-up: uploads the bag table, sets NCCL up for these sizes
+            for _ in range(max(1, warmup)):
+                sharded_forward_bags_batched(bops, self.xs, self.offs, group)
+        torch.cuda.current_stream(bops.device).wait_stream(side)
+        torch.cuda.synchronize(bops.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outs = sharded_forward_bags_batched(bops, self.xs, self.offs, group)
+
+    @torch.no_grad()
+    def replay(self):
+        """Runs the captured step on the current stream; returns the (static) output tensors of the step."""
+        self.graph.replay()
+        return self.outs
 
 
 def _all_gather(rec: torch.Tensor, group) -> Tuple[torch.Tensor, int]:
