@@ -13,7 +13,7 @@ namespace dsmil {
 namespace sm100 {
 
 constexpr int kAttRows = 128;          // rows per attend tile (same tiling as phase 1)
-constexpr int kMaxRecPerBag = 128;
+constexpr int kMaxRecPerBag = 160;         // >= SM count: the fused attention pass emits one record per (CTA, bag)
 
 struct AttendArgs {
   const BagDev* bags;
@@ -263,18 +263,20 @@ struct FinalizeArgs {
   int ext_P, ext_nb;
 };
 
-constexpr int kFinSlices = 8;
+constexpr int kFinSlices = 32;
 
-// grid = (kFinSlices, nb).  Every CTA derives (M, S) of its bag from the <=128 partial records, normalises
-// its share of A, combines its share of the B columns (records summed in a fixed interleaved order ->
-// deterministic) and contributes a partial Conv1d dot product; the last CTA of the bag to finish adds the
-// kFinSlices partials in slice order (dsmil.py:59-61) and writes the critical indices.
+// grid = (kFinSlices, nb).  Every CTA derives (M, S) of its bag from the partial records, normalises its share of the
+// rows of A, combines its share of the B columns -- eight threads per column, each summing every eighth record with
+// all its loads in flight, partials added in a fixed order (deterministic) -- and contributes a partial Conv1d dot
+// product; the last CTA of the bag to finish adds the kFinSlices partials in slice order (dsmil.py:59-61) and writes
+// the critical indices.  (r1 ran 8 slices with two threads per column: 128 CTAs of latency-bound serial work, 19-21 us
+// for a 16-bag step; profiles/r2_bench_history.md.)
 __global__ void __launch_bounds__(256)
 k_finalize_b(const FinalizeArgs a) {
   __shared__ float sw[kMaxRecPerBag][kMaxC];
   __shared__ float sM[kMaxC], sS[kMaxC];
-  __shared__ float s_part[256];
-  __shared__ float red[8][kMaxC];
+  __shared__ float s_part[8][32];
+  __shared__ float red[kMaxC];
   __shared__ unsigned int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = a.C, D = a.D;
@@ -285,20 +287,20 @@ k_finalize_b(const FinalizeArgs a) {
   const float* recs = ext ? a.recs + static_cast<size_t>(bag) * rstride : a.recs + static_cast<size_t>(bg.rec_off) * rstride;
   const size_t pstride = ext ? rstride * a.ext_nb : rstride;     // distance between consecutive records of the bag
   const int P = ext ? a.ext_P : bg.nrec;
-  // (M, S): thread (k, j) scans records j, j+32, ... ; fixed-order combine
+  // (M, S): warp k scans the records of class k; fixed-order combine
   for (int k = warp; k < C; k += 8) {
     float m = -INFINITY;
     for (int p = lane; p < P; p += 32) m = fmaxf(m, recs[p * pstride + k]);
     m = warp_max(m);
-    float s = 0.f;
+    float sacc = 0.f;
     for (int p = lane; p < P; p += 32) {
       const float mp = recs[p * pstride + k];
       const float w = (mp == -INFINITY) ? 0.f : expf(mp - m);
       sw[p][k] = w;
-      s = fmaf(recs[p * pstride + C + k], w, s);
+      sacc = fmaf(recs[p * pstride + C + k], w, sacc);
     }
-    s = warp_sum(s);
-    if (lane == 0) { sM[k] = m; sS[k] = s; }
+    sacc = warp_sum(sacc);
+    if (lane == 0) { sM[k] = m; sS[k] = sacc; }
   }
   __syncthreads();
   if (a.emit == nullptr) {  // normalise this slice's rows of A
@@ -311,40 +313,44 @@ k_finalize_b(const FinalizeArgs a) {
       Ab[i] = __fdiv_rn(expf(Ab[i] - sM[k]), sS[k]);
     }
   }
-  // B columns of this slice: element e = k*D + d; two threads per element split the records (even / odd)
+  // B columns of this slice: element e = k*D + d; thread (column = tid & 31, record phase rp = tid >> 5)
   const int CD = C * D;
   const int eps = (CD + kFinSlices - 1) / kFinSlices;
   const int e_lo = eps * blockIdx.x, e_hi = (e_lo + eps) < CD ? (e_lo + eps) : CD;
+  const int rp = tid >> 5;
   float ppart[kMaxC];
 #pragma unroll
   for (int k = 0; k < kMaxC; ++k) ppart[k] = 0.f;
-  for (int base = e_lo; base < e_hi; base += 128) {
-    const int e = base + (tid & 127);
-    const int par = tid >> 7;
+  for (int base = e_lo; base < e_hi; base += 32) {
+    const int e = base + lane;
     float acc = 0.f;
     if (e < e_hi) {
       const int k = e / D;
       const float* col = recs + 2 * C + e;
-      int p = par;
 #pragma unroll 1
-      for (; p + 14 < P; p += 16) {   // 8 independent loads in flight
+      for (int p0 = rp; p0 < P; p0 += 64) {   // up to 8 loads in flight per thread: records p0, p0+8, ..., p0+56
         float v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = col[static_cast<size_t>(p + 2 * u) * pstride];
+        for (int u = 0; u < 8; ++u) v[u] = (p0 + 8 * u < P) ? col[static_cast<size_t>(p0 + 8 * u) * pstride] : 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc = fmaf(v[u], sw[p + 2 * u][k], acc);
+        for (int u = 0; u < 8; ++u)
+          if (p0 + 8 * u < P) acc = fmaf(v[u], sw[p0 + 8 * u][k], acc);
       }
-      for (; p < P; p += 2) acc = fmaf(col[static_cast<size_t>(p) * pstride], sw[p][k], acc);
     }
-    if (par == 1) s_part[tid & 127] = acc;
+    s_part[rp][lane] = acc;
     __syncthreads();
-    if (par == 0 && e < e_hi && a.emit != nullptr) {
-      a.emit[static_cast<size_t>(bag) * rstride + 2 * C + e] = acc + s_part[tid];
-    } else if (par == 0 && e < e_hi) {
-      const int k = e / D;
-      const float b = __fdiv_rn(acc + s_part[tid], sS[k]);
-      a.B[static_cast<size_t>(bag) * CD + e] = b;
-      for (int kk = 0; kk < C; ++kk) ppart[kk] = fmaf(__ldg(a.Wf + static_cast<size_t>(kk) * CD + e), b, ppart[kk]);
+    if (rp == 0 && e < e_hi) {
+      float tot = s_part[0][lane];
+#pragma unroll
+      for (int r = 1; r < 8; ++r) tot += s_part[r][lane];
+      if (a.emit != nullptr) {
+        a.emit[static_cast<size_t>(bag) * rstride + 2 * C + e] = tot;
+      } else {
+        const int k = e / D;
+        const float bval = __fdiv_rn(tot, sS[k]);
+        a.B[static_cast<size_t>(bag) * CD + e] = bval;
+        for (int kk = 0; kk < C; ++kk) ppart[kk] = fmaf(__ldg(a.Wf + static_cast<size_t>(kk) * CD + e), bval, ppart[kk]);
+      }
     }
     __syncthreads();
   }
@@ -355,18 +361,16 @@ k_finalize_b(const FinalizeArgs a) {
     }
     return;
   }
-  // partial Conv1d logits of this slice (fixed reduction order inside the CTA)
-  for (int kk = 0; kk < C; ++kk) {
-    const float v = warp_sum(ppart[kk]);
-    if (lane == 0) red[warp][kk] = v;
+  // partial Conv1d logits of this slice: the contributions live in warp 0 (fixed shuffle order)
+  if (warp == 0) {
+    for (int kk = 0; kk < C; ++kk) {
+      const float v = warp_sum(ppart[kk]);
+      if (lane == 0) red[kk] = v;
+    }
   }
   __syncthreads();
   float* part = a.pred_part + (static_cast<size_t>(bag) * kFinSlices + blockIdx.x) * kMaxC;
-  if (tid < C) {
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += red[w][tid];
-    part[tid] = s;
-  }
+  if (tid < C) part[tid] = red[tid];
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = atomicAdd(a.counters + bag, 1u);
@@ -375,9 +379,9 @@ k_finalize_b(const FinalizeArgs a) {
   __threadfence();
   if (tid < C) {
     const volatile float* pp = a.pred_part + static_cast<size_t>(bag) * kFinSlices * kMaxC;
-    float s = 0.f;
-    for (int sl = 0; sl < kFinSlices; ++sl) s += pp[sl * kMaxC + tid];
-    a.pred[static_cast<size_t>(bag) * C + tid] = s + __ldg(a.bf + tid);
+    float sacc = 0.f;
+    for (int sl = 0; sl < kFinSlices; ++sl) sacc += pp[sl * kMaxC + tid];
+    a.pred[static_cast<size_t>(bag) * C + tid] = sacc + __ldg(a.bf + tid);
     if (a.crit) a.crit[static_cast<size_t>(bag) * C + tid] = key_row(a.keys[static_cast<size_t>(bag) * kMaxC + tid]);
   }
 }

@@ -15,17 +15,18 @@
 //   * layer 2 as before from TMEM (H1 -> bf16 hi/lo -> tcgen05.st), its accumulator ALIASES the drained layer-1
 //     accumulator of the same tile, which frees the TMEM columns the X operand stages need.
 //
-//   warps: 0-7 epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2) | 8-23 converters in 2 groups of 8
-//          (two warps per lane quadrant, each taking 16 of a box's 32 k; group g takes the boxes g, g+2, ... of the
-//          CTA's box sequence and alternates between ITS two TMEM operand stages, so it can convert and store box
-//          m+1 while box m waits for both CTAs / the tensor pipe) | 24 MMA issuer (leader CTA only) | 25 TMA producer |
+//   warps: 0-7 epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2) | 8-23 converters in 4 groups of 4
+//          (one warp per lane quadrant; group g takes the boxes g, g+4, ... of the CTA's box sequence and owns TMEM
+//          operand stage g: four boxes are in conversion at any time, which is what hides the per-box chain
+//          TMA -> LDS -> split -> tcgen05.st -> cross-CTA arrive -> MMA -> commit; measured variants in
+//          profiles/r2_bench_history.md) | 24 MMA issuer (leader CTA only) | 25 TMA producer |
 //          26 TMEM allocation + weight load | 27 idle
 //   smem : W1 half (D/64 x 16 KB) | W2 half (2 x 16 KB) | X staging 3 slots x 16 KB | Wi | score partials
 //   TMEM : acc0 128 | acc1 128 (layer-1 accumulator, then layer-2 accumulator of the same tile) | A2 hi 64 | A2 lo 64 |
-//          X operand stages 4 x (hi 16 + lo 16): stage = box % 4
-//   barriers: a staging slot (box % 3) is filled for one group and then the other, so its full/empty barriers are
-//          indexed by box % 6 (fixed group, fixed slot): every mbarrier has ONE waiting party that sees every phase
-//          in order (a barrier per slot would let a group wait for use u+1 before use u has completed)
+//          X operand stages 4 x (hi 16 + lo 16): stage = box % 4 = group
+//   barriers: a staging slot (box % 3) serves the four groups in turn, so its full/empty barriers are indexed by
+//          box % 12 (fixed group, fixed slot): every mbarrier has ONE waiting party that sees every phase in order
+//          (a barrier per slot would let a group wait for use u+1 before use u has completed)
 //   cross-CTA: converters / epilogue warps of the second CTA arrive REMOTELY (mapa) on the leader's barriers; the MMA
 //          issuer answers with multicast tcgen05.commit on the barrier of the same offset in both CTAs.
 // Mechanisms first validated in isolation by tools/probe_pair.cu.
@@ -59,12 +60,12 @@ using sm100::TileCursor;
 constexpr int kTileM = 128;
 constexpr int kBoxK = 32;                         // floats per TMA box row = 128 B = one swizzle row
 constexpr int kBoxBytes = kTileM * kBoxK * 4;     // 16 KB
-constexpr int kGroups = 2;                        // converter groups (box n belongs to group n % 2)
+constexpr int kGroups = 4;                        // converter groups (box n belongs to group n % 4)
 constexpr int kSlots = 3;                         // X staging slots (box n lands in slot n % 3)
-constexpr int kXBars = 6;                         // full/empty barrier index = n % 6 (lcm of the two)
-constexpr int kTStages = 4;                       // TMEM operand stages (box n is stored to stage n % 4)
+constexpr int kXBars = 12;                        // full/empty barrier index = n % 12 (lcm of the two)
+constexpr int kTStages = 4;                       // TMEM operand stages (box n is stored to stage n % 4 = its group)
 constexpr int kWChunk = 2 * 64 * 128;             // per 64-k chunk and CTA: hi tile [64 features x 128 B] + lo tile
-constexpr int kEpiWarps = 8, kConvWarps = 8 * kGroups;
+constexpr int kEpiWarps = 8, kConvWarps = 4 * kGroups;
 constexpr int kWarpConv0 = kEpiWarps, kWarpMma = kEpiWarps + kConvWarps, kWarpProd = kWarpMma + 1, kWarpAux = kWarpMma + 2;
 constexpr int kThreads = 32 * (kEpiWarps + kConvWarps + 4);     // 896
 constexpr int kSmemBags = 96;
@@ -74,11 +75,14 @@ __device__ __forceinline__ uint32_t cta_rank() { uint32_t r; asm volatile("mov.u
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of the pair (release at cluster scope)
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the pair.  Default (.release.cta) semantics, as
+// CUTLASS' ClusterBarrier::arrive(cta_id): what the arrival publishes is TMEM content, ordered by tcgen05.wait::st +
+// tcgen05.fence::before_thread_sync.  A `.release.cluster` arrive costs ~1.4 us per box here (measured,
+// profiles/r2_ptrace_pair.md) -- the peer CTA then paces the pair.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar, uint32_t my_rank) {
   if (my_rank == 0) mbar_arrive(bar); else mbar_arrive_remote(bar, 0);
@@ -88,25 +92,28 @@ template <bool CL>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t sleep_ns = 0) {
   uint32_t done = 0, spins = 0;
   while (true) {
-    if (CL)
-      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                   : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    else
-      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+    (void)CL;   // (arrivals from the peer CTA need no cluster-scope acquire either: see mbar_arrive_remote)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                    : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) break;
     if (sleep_ns) __nanosleep(sleep_ns);
     if (++spins > (1u << 26)) __trap();          // a protocol bug must not hang the GPU
   }
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-               ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+// (L2 cache hint: evict-last -- the attend kernel re-reads X, walking the tiles backwards from the most recent one)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+               ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "l"(pol) : "memory");
 }
 // L2 prefetch of a box (no shared memory, no barrier): issued one tile ahead so that the staging loads, which can only
 // be one box per converter group in flight, pay L2 latency instead of HBM latency
 __device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
+// L2 prefetch of CONTIGUOUS bytes (a 128-row tile of X is one contiguous 128 * D * 4-byte range): sequential DRAM pages
+// instead of the 128 scattered 128-byte rows a box prefetch touches
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrive::one on `bar` in BOTH CTAs when the MMAs retire
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -140,6 +147,7 @@ struct PairArgs {
   unsigned long long* keys; // [nb][kMaxC]
   float* Q;                 // tile-blocked [tile][128 col][128 row]
   long long* dbg;           // optional timeline of CTA 0 (clock64 stamps; tools/ptrace.py), NULL = off
+  int flags;                // experiments (DSMIL_B200_PAIR_FLAGS): 1 no L2 prefetch, 4 producer polls without back-off
 };
 // trace slots [role 8][event 8][index 128], stamps = %globaltimer (ns; comparable across the two CTAs):
 // role 0 converter warp 0 of CTA 0, 1 MMA issuer, 2 epilogue warp 0 of CTA 0, 3 producer of CTA 0,
@@ -163,7 +171,7 @@ inline size_t pair_smem_bytes(int C, int D) {
   return pair_wimg_rank_bytes(D) + kSlots * kBoxBytes + sizeof(float) * ct * D + sizeof(float) * 2 * 4 * kTileM * ct + 1024;
 }
 inline bool pair_supported(const dsmil_params_t* p) {
-  return p->nonlinear && !p->passing_v && p->D % 64 == 0 && p->D >= 128 && p->D <= kMaxD && p->C <= 4 &&
+  return p->nonlinear && !p->passing_v && p->D % 128 == 0 && p->D >= 128 && p->D <= kMaxD && p->C <= 4 &&
          pair_smem_bytes(p->C, p->D) + 5632 <= 232448;
 }
 
@@ -206,8 +214,8 @@ k_fwd_pair(const PairArgs a) {
     for (int i = tid; i < a.nb; i += kThreads) s_bags[i] = a.bags[i];
   const BagDev* tbl = tbl_in_smem ? s_bags : a.bags;
   if (tid == 0) {
-    for (int s = 0; s < kXBars; ++s) { mbar_init(bar(XS_FULL + s), 1); mbar_init(bar(XS_EMPTY + s), 8); }
-    for (int s = 0; s < kTStages; ++s) { mbar_init(bar(XT_FULL + s), 16); mbar_init(bar(XT_EMPTY + s), 1); }
+    for (int s = 0; s < kXBars; ++s) { mbar_init(bar(XS_FULL + s), 1); mbar_init(bar(XS_EMPTY + s), 4); }
+    for (int s = 0; s < kTStages; ++s) { mbar_init(bar(XT_FULL + s), 8); mbar_init(bar(XT_EMPTY + s), 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(H1_FULL + b), 1); mbar_init(bar(Q_FULL + b), 1); mbar_init(bar(ACC_EMPTY + b), 2 * kEpiWarps);
       mbar_init(bar(SC_DONE + b), kConvWarps);
@@ -243,6 +251,7 @@ k_fwd_pair(const PairArgs a) {
     // per real load, one tile ahead (the few boxes in flight then pay L2 latency, not HBM latency) =====
     if (lane == 0) {
       TileCursor cur(tbl, 0, a.nb), cur_pf(tbl, 0, a.nb);
+      const uint64_t pol_keep = sm100::l2_policy_evict_last();
       uint32_t n = 0;
       for (int j = 0; j < niter; ++j) {
         const int tile = 2 * (cl + j * ncl) + static_cast<int>(rank);
@@ -253,95 +262,125 @@ k_fwd_pair(const PairArgs a) {
         const int row0 = (tile - bp->tile_off) * kTileM;
         const int ptile = 2 * (cl + (j + 1) * ncl) + static_cast<int>(rank);
         const bool pf = j + 1 < niter && ptile < a.ntiles;
-        const CUtensorMap* ptm = tm;
-        int prow0 = 0;
+        const uint8_t* pf_ptr = nullptr;             // next tile of this CTA as a contiguous byte range
+        uint32_t pf_bytes = 0;
         if (pf) {
           cur_pf.seek(ptile);
-          ptm = a.tmaps + cur_pf.bag;
-          prow0 = (ptile - tbl[cur_pf.bag].tile_off) * kTileM;
+          const BagDev* pb = tbl + cur_pf.bag;
+          const long long prow0 = static_cast<long long>(ptile - pb->tile_off) * kTileM;
+          const long long prows = (pb->N - prow0) < kTileM ? (pb->N - prow0) : kTileM;
+          pf_ptr = reinterpret_cast<const uint8_t*>(pb->X + prow0 * D);
+          pf_bytes = static_cast<uint32_t>(prows * D * 4);
         }
+        const uint32_t pf_step = static_cast<uint32_t>(kTileM * D * 4) / nboxes;     // 16 KB at D = 512
         for (int kb = 0; kb < nboxes; ++kb, ++n) {
           if (n >= kSlots) {                         // slot last used by box n-3: wait until its group has read it
             const uint32_t pn = n - kSlots;
-            mbar_wait<false>(bar(XS_EMPTY + pn % kXBars), (pn / kXBars) & 1, 32);
+            mbar_wait<false>(bar(XS_EMPTY + pn % kXBars), (pn / kXBars) & 1, (a.flags & 4) ? 0 : 32);
           }
           if (blockIdx.x == 0) PAIR_TRACE(3, 0, n);
           mbar_expect_tx(bar(XS_FULL + n % kXBars), kBoxBytes);
-          tma_load_2d(smem_u32(sX + (n % kSlots) * kBoxBytes), tm, kb * kBoxK, row0, bar(XS_FULL + n % kXBars));
-          if (pf) tma_prefetch_2d(ptm, kb * kBoxK, prow0);
-          if (j == 0 && kb == kSlots - 1)            // the first tile itself: start its later boxes towards L2 now
-            for (int k2 = kSlots; k2 < nboxes; ++k2) tma_prefetch_2d(tm, k2 * kBoxK, row0);
+          tma_load_2d(smem_u32(sX + (n % kSlots) * kBoxBytes), tm, kb * kBoxK, row0, bar(XS_FULL + n % kXBars), pol_keep);
+          if (pf && !(a.flags & 1) && kb * pf_step < pf_bytes) {
+            const uint32_t off = kb * pf_step;
+            bulk_prefetch_l2(pf_ptr + off, (pf_bytes - off) < pf_step ? (pf_bytes - off) : pf_step);
+          }
+          if (j == 0 && kb == kSlots - 1 && !(a.flags & 1)) {          // the first tile itself: start the rest of it towards L2 now
+            const long long rws = (bp->N - row0) < kTileM ? (bp->N - row0) : kTileM;
+            const uint8_t* t0 = reinterpret_cast<const uint8_t*>(bp->X + static_cast<long long>(row0) * D);
+            const uint32_t tb = static_cast<uint32_t>(rws * D * 4);
+            for (uint32_t off = 0; off < tb; off += 32768) bulk_prefetch_l2(t0 + off, (tb - off) < 32768u ? (tb - off) : 32768u);
+          }
         }
       }
     }
   } else if (warp >= kWarpConv0 && warp < kWarpMma) {
-    // ===== converters: lane = row of the quadrant; warp (g, h, q): group g takes boxes g, g+2, ...; k-half h =====
-    const int cw = warp - kWarpConv0, q = cw & 3, h = (cw >> 2) & 1, g = cw >> 3;
+    // ===== converters: lane = row of the quadrant; warp (g, q): group g takes boxes g, g+4, ...; TMEM stage g =====
+    const int cw = warp - kWarpConv0, q = cw & 3, g = cw >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t sx_u32 = smem_u32(sX) + row * 128;
     const uint32_t swi_u32 = smem_u32(sWi);
     const uint32_t total = static_cast<uint32_t>(niter) * nboxes;
+    const uint32_t tstage = tm_x + lane_sel + g * 32;
     float sc[CT];
 #pragma unroll
     for (int k = 0; k < CT; ++k) sc[k] = 0.f;
-    int j = 0, kb = g;                              // (tile iteration, box in tile) of box n; nboxes is even and >= 4
-    const int trole = (lane == 0 && blockIdx.x < 2 && (cw == 0 || cw == 15)) ? (cw == 0 ? (blockIdx.x ? 4 : 0) : (blockIdx.x ? 6 : 5)) : -1;
+    int j = 0, kb = g;                              // (tile iteration, box in tile) of box n; nboxes % 4 == 0
     bool valid = 2 * cl + static_cast<int>(rank) < a.ntiles;
+    const int trole = (lane == 0 && blockIdx.x < 2 && (cw == 0 || cw == 15)) ? (cw == 0 ? (blockIdx.x ? 4 : 0) : (blockIdx.x ? 6 : 5)) : -1;
     uint32_t m = 0;
     for (uint32_t n = g; n < total; n += kGroups, ++m) {
-      uint32_t hi[8], lo[8];
-      const uint32_t fb = n % kXBars, stage = n % kTStages;
+      const uint32_t fb = n % kXBars;
       if (valid) {
         if (trole >= 0) PAIR_TRACE(trole, 0, m);
         mbar_wait<false>(bar(XS_FULL + fb), (n / kXBars) & 1);
         if (trole >= 0) PAIR_TRACE(trole, 1, m);
         PAIR_TRACE_ALL(0, n, cw);
-        const uint32_t rowb = sx_u32 + (n % kSlots) * kBoxBytes;
+      }
+      const uint32_t rowb = sx_u32 + (n % kSlots) * kBoxBytes;
 #pragma unroll
-        for (int ii = 0; ii < 4; ++ii) {
-          const int i = 4 * h + ii;                                           // 16-byte unit of the box row: floats 4i .. 4i+3
-          const float4 x = lds128(rowb + (((i ^ (row & 7)) & 7) << 4));
+      for (int h = 0; h < 2; ++h) {                 // two halves of 16 k: 8 + 8 TMEM columns each
+        uint32_t hi[8], lo[8];
+        if (valid) {
+          float4 x[4];
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii)              // the four loads are issued back to back, then used
+            x[ii] = lds128(rowb + ((((4 * h + ii) ^ (row & 7)) & 7) << 4));        // floats 4i .. 4i+3, i = 4h+ii
           if (do_scores) {
 #pragma unroll
             for (int k = 0; k < CT; ++k) {
-              const float4 w = lds128(swi_u32 + static_cast<uint32_t>(k * D + kb * kBoxK + 4 * i) * 4u);   // broadcast
+              float4 w[4];
+#pragma unroll
+              for (int ii = 0; ii < 4; ++ii)
+                w[ii] = lds128(swi_u32 + static_cast<uint32_t>(k * D + kb * kBoxK + 16 * h + 4 * ii) * 4u);   // broadcast
               float sv = sc[k];
-              sv = fmaf(x.x, w.x, sv); sv = fmaf(x.y, w.y, sv); sv = fmaf(x.z, w.z, sv); sv = fmaf(x.w, w.w, sv);
+#pragma unroll
+              for (int ii = 0; ii < 4; ++ii) {
+                sv = fmaf(x[ii].x, w[ii].x, sv); sv = fmaf(x[ii].y, w[ii].y, sv);
+                sv = fmaf(x[ii].z, w[ii].z, sv); sv = fmaf(x[ii].w, w[ii].w, sv);
+              }
               sc[k] = sv;
             }
           }
-          const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
-          const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
-          const __nv_bfloat162 l01 = __floats2bfloat162_rn(x.x - __uint_as_float(u01 << 16), x.y - __uint_as_float(u01 & 0xffff0000u));
-          const __nv_bfloat162 l23 = __floats2bfloat162_rn(x.z - __uint_as_float(u23 << 16), x.w - __uint_as_float(u23 & 0xffff0000u));
-          hi[2 * ii] = u01; hi[2 * ii + 1] = u23;
-          lo[2 * ii] = *reinterpret_cast<const uint32_t*>(&l01); lo[2 * ii + 1] = *reinterpret_cast<const uint32_t*>(&l23);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(XS_EMPTY + fb));                    // staging slot read by this warp
-      } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { hi[i] = 0u; lo[i] = 0u; }
+          for (int ii = 0; ii < 4; ++ii) {
+            const float4 xv = x[ii];
+            const __nv_bfloat162 h01 = __floats2bfloat162_rn(xv.x, xv.y), h23 = __floats2bfloat162_rn(xv.z, xv.w);
+            const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
+            const __nv_bfloat162 l01 = __floats2bfloat162_rn(xv.x - __uint_as_float(u01 << 16), xv.y - __uint_as_float(u01 & 0xffff0000u));
+            const __nv_bfloat162 l23 = __floats2bfloat162_rn(xv.z - __uint_as_float(u23 << 16), xv.w - __uint_as_float(u23 & 0xffff0000u));
+            hi[2 * ii] = u01; hi[2 * ii + 1] = u23;
+            lo[2 * ii] = *reinterpret_cast<const uint32_t*>(&l01); lo[2 * ii + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { hi[i] = 0u; lo[i] = 0u; }
+        }
+        if (h == 0) {
+          if (trole >= 0) PAIR_TRACE(trole, 2, m);
+          mbar_wait<false>(bar(XT_EMPTY + g), (m & 1) ^ 1, 32);           // operand stage released by the MMAs of box n-4
+          if (trole >= 0) PAIR_TRACE(trole, 3, m);
+          PAIR_TRACE_ALL(1, n, cw);
+          tc_fence_after();
+        } else if (valid) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(XS_EMPTY + fb));                  // staging slot read by this warp
+        }
+        DSMIL_TMEM_ST8(tstage + h * 8, hi);
+        DSMIL_TMEM_ST8(tstage + 16 + h * 8, lo);
       }
-      if (trole >= 0) PAIR_TRACE(trole, 2, m);
-      mbar_wait<false>(bar(XT_EMPTY + stage), ((n / kTStages) & 1) ^ 1, 32);   // operand stage released by the MMAs
-      if (trole >= 0) PAIR_TRACE(trole, 3, m);
-      PAIR_TRACE_ALL(1, n, cw);
-      tc_fence_after();
-      DSMIL_TMEM_ST8(tm_x + lane_sel + stage * 32 + h * 8, hi);
-      DSMIL_TMEM_ST8(tm_x + lane_sel + stage * 32 + 16 + h * 8, lo);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader(bar(XT_FULL + stage), rank);
+      if (lane == 0) mbar_arrive_leader(bar(XT_FULL + g), rank);
       if (trole >= 0) PAIR_TRACE(trole, 4, m);
       PAIR_TRACE_ALL(2, n, cw);
-      // next box of this group; on leaving a tile hand the score partial (group g, k-half h) to the epilogue
+      // next box of this group; on leaving a tile hand the score partial of group g to the epilogue
       const int kb_next = kb + kGroups;
       if (kb_next >= nboxes) {
         if (do_scores) {
-          float* dst = sSc + ((static_cast<size_t>(j & 1) * 4 + (g * 2 + h)) * kTileM + row) * CT;
+          float* dst = sSc + ((static_cast<size_t>(j & 1) * 4 + g) * kTileM + row) * CT;
 #pragma unroll
           for (int k = 0; k < CT; ++k) { dst[k] = sc[k]; sc[k] = 0.f; }
           __syncwarp();
@@ -424,7 +463,7 @@ k_fwd_pair(const PairArgs a) {
         nrow = static_cast<long long>(tile - bg.tile_off) * kTileM + row_in_tile;
         live = nrow < bg.N;
       }
-      // ---- instance scores of this tile: four (box parity, k-half) partials summed in a fixed order + bias ----
+      // ---- instance scores of this tile: four partials (boxes kb = g mod 4) summed in a fixed order + bias ----
       if (do_scores && valid) {
         mbar_wait<false>(bar(SC_DONE + b), ub, 64);
         if (half == 0) {
@@ -585,7 +624,9 @@ inline int launch_fwd_pair(const dsmil_params_t* p, const BagDev* bags_dev, cons
                            float* classes, unsigned long long* keys, float* Q, const uint8_t* wimg, int num_sms,
                            cudaStream_t st) {
   const int D = p->D, C = p->C;
-  PairArgs a{bags_dev, tmaps_dev, nb, ntiles, D, C, p->Wi, p->bi, p->b1, p->b2, wimg, classes, keys, Q, sm100::g_trace_buf};
+  static int flags = -1;
+  if (flags < 0) { const char* e = getenv("DSMIL_B200_PAIR_FLAGS"); flags = e ? atoi(e) : 0; }
+  PairArgs a{bags_dev, tmaps_dev, nb, ntiles, D, C, p->Wi, p->bi, p->b1, p->b2, wimg, classes, keys, Q, sm100::g_trace_buf, flags};
   const size_t smem = pair_smem_bytes(C, D);
   const int nsuper = (ntiles + 1) / 2;
   const int pairs = std::max(1, std::min(nsuper, num_sms / 2));
