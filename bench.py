@@ -583,6 +583,33 @@ def run_ours(args):
                   "step_launch": "CUDA graph replay" if gplan is not None else "eager"}
         del giant
 
+    # ---- per-phase breakdown of one host-launched sharded step (CUDA events on the launch stream, max over ranks) -----
+    breakdown = None
+    if world > 1 and bops is not None and not args.no_extras:
+        from dsmil_wsi_b200.sharded import _all_gather
+        names = ["phase1 (scores+keys+Q-MLP+candidates)", "all_gather candidates", "phase2 (merge+attend+local record)",
+                 "all_gather records", "phase3 (combine+normalise+bag logits)"]
+        acc = [0.0] * 5
+        reps_b = 10
+        with torch.no_grad():
+            for it_b in range(reps_b + 2):
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+                bops.begin(bags, offsets)
+                ev[0].record(); cand = bops.phase1()
+                ev[1].record(); cands_all, Gg = _all_gather(cand.view(-1), None)
+                ev[2].record(); recs_l = bops.phase2(cands_all, Gg)
+                ev[3].record(); recs_all, Gg = _all_gather(recs_l.view(-1), None)
+                ev[4].record(); bops.phase3(recs_all, Gg)
+                ev[5].record()
+                torch.cuda.synchronize()
+                if it_b >= 2:
+                    for i in range(5):
+                        acc[i] += ev[i].elapsed_time(ev[i + 1]) / reps_b
+        tb = torch.tensor(acc, device=dev)
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        breakdown = {"unit": "ms", "launch": "eager (host-launched), events between the five calls, max over ranks",
+                     **{n: float(v) for n, v in zip(names, tb.tolist())}, "sum": float(tb.sum().item())}
+
     # ---- multi-rank parity check (outside every timed region): one sharded forward against the CPU oracle ------
     parity = None
     if world > 1 and not args.no_extras:
@@ -626,10 +653,19 @@ def run_ours(args):
                           "l2_policy": f"inputs larger than L2: {nb} bags x {NBAG * D * 4 / 1e6:.1f} MB per rank cycled",
                           "forward_path": int(lib.dsmil_forward_path(ctypes.byref(_lib.DsmilParams(D, C, 1, 0)), NBAG))},
                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches * world,
-               "clocks": clocks, "strong_n100k": strong, "parity_check": parity, "extras": extras}
+               "clocks": clocks, "strong_n100k": strong, "parity_check": parity, "step_breakdown": breakdown,
+               "extras": extras}
         print(json.dumps(out))
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs that captured NCCL collectives keep communicator resources alive; tearing the process group down
+        # underneath them can block forever (seen once: the JSON line was out, the process never exited).  Drop the
+        # graphs, meet at a barrier, flush, and leave without running destructors.
+        plan = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -644,7 +680,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="multi-GPU: host-launched step instead of the CUDA-graph replay")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra workloads (eager-GPU baseline, N=8192, "
                     "N=15000 training step, N=100k strong scaling, multi-rank parity check)")
-    ap.add_argument("--giant-bags", type=int, default=4, help="N=100 000 bags per step of the strong-scaling workload")
+    ap.add_argument("--giant-bags", type=int, default=16, help="N=100 000 bags per step of the strong-scaling workload")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

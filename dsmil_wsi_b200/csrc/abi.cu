@@ -1033,7 +1033,8 @@ int dsmil_shard_bags_phase1(const dsmil_params_t* p, const float* const* Xs, con
   }
   DSMIL_CUDA_OK(cudaMemsetAsync(w.base.keys, 0, sizeof(unsigned long long) * (kMaxC + 1) * nb, st));
   uint8_t* img = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(w.base.wimg) + 1023) & ~uintptr_t(1023));
-  if ((rc = sm100::launch_prep_wimg(p, img, st))) return rc;
+  // (a captured serving loop also reuses the weight images of the preceding eager call: re-capture after a weight update)
+  if (!stream_is_capturing(st) && (rc = sm100::launch_prep_wimg(p, img, st))) return rc;
   if ((rc = sm100::launch_qmlp(p, w.base.table, 0, nb, 0, tiles, classes, w.base.keys, w.base.Q, nullptr, img, num_sms(), st, 1)))
     return rc;
   sm100::k_gather_cand_b<<<dim3(p->C, nb), kQ, 0, st>>>(w.base.table, w.base.keys, classes, w.base.Q, 1, w.row_offsets, p->C,

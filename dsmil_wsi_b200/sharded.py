@@ -258,8 +258,9 @@ class ShardedBagsGraph:
     """Fixed-shape serving loop: the whole row-sharded step -- three library calls and the two NCCL all-gathers -- is
     captured ONCE in a CUDA graph and replayed, so a step costs one graph launch instead of ~12 host-driven launches
     (the sharded step is latency-, not bandwidth-bound: a few KB cross NVLink).  The bags' storage and shapes must
-    stay the same between replays (write new features INTO the same tensors); every rank must build and replay the
-    graph collectively."""
+    stay the same between replays (write new features INTO the same tensors), and so must the weights (the captured
+    step reuses the bag table and the bf16 weight images of the warm-up run: build a new graph after a weight update);
+    every rank must build and replay the graph collectively."""
 
     def __init__(self, bops: "CudaShardBagOps", X_locals, row_offsets, group=None, warmup: int = 3):
         self.bops, self.xs, self.offs, self.group = bops, list(X_locals), list(row_offsets), group
