@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdsmil_b200.so")
+# DSMIL_B200_LIBPATH: load another build of the SAME sources (kernel tuning experiments, tools/); never a fallback
+LIB_PATH = os.environ.get("DSMIL_B200_LIBPATH") or os.path.join(_HERE, "lib", "libdsmil_b200.so")
 
 c_float_p = C.c_void_p  # device pointers travel as integers
 c_i64 = C.c_int64

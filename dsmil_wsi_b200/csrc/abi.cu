@@ -186,21 +186,6 @@ static bool stream_is_capturing(cudaStream_t st) {
   return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
 }
 
-// Attention pass folded into the epilogue warps of k_qmlp_sm100 (FUSE instantiations).  Measured (profiles/
-// r2_bench_history.md): in a multi-wave batch the extra work makes the epilogue the pacing role (242 us vs 118 + 74 us per
-// 16-bag step), but when every CTA has at most ONE tile -- a single bag of up to num_sms * 128 rows, i.e. the call the
-// reference's drivers make (train_tcga.py:98) -- the attention pass simply follows phase 1 in the same kernel, reading
-// X from L2: one launch less and no second HBM pass.  mode 0 = never, 1 = single-wave calls only (default), 2 = always.
-static int fuse_mode() {
-  static int mode = -1;
-  if (mode < 0) { const char* e = getenv("DSMIL_B200_FUSE"); mode = e ? atoi(e) : 1; }
-  return mode;
-}
-static bool use_fuse(const dsmil_params_t* p, int total_tiles) {
-  const int mode = fuse_mode();
-  if (mode <= 0 || !use_sm100(p) || !sm100::qmlp_fuse_supported(p)) return false;
-  return mode >= 2 || total_tiles <= num_sms();
-}
 static bool use_pair(const dsmil_params_t* p) {
   // CTA-pair phase 1 (fwd_pair.cuh): parity-green, but not yet faster than k_qmlp_sm100 (profiles/r2_bench_history.md),
   // so it is opt-in: DSMIL_B200_PAIR=1
@@ -379,11 +364,7 @@ static BagsWs carve_bags(const dsmil_params_t* p, const int64_t* Ns, int nb, boo
   Carver c(ws, cap);
   BagsWs w;
   int64_t total = 0, nrec = 0;
-  for (int b = 0; b < nb; ++b) {      // the fused attention pass may use up to one record per (SM, bag)
-    total += Ns[b];
-    const int64_t t = (Ns[b] + sm100::kTileM - 1) / sm100::kTileM;
-    nrec += std::max<int64_t>(recs_for_bag(Ns[b]), std::min<int64_t>(t, sm100::kMaxRecPerBag));
-  }
+  for (int b = 0; b < nb; ++b) { total += Ns[b]; nrec += recs_for_bag(Ns[b]); }
   w.table = c.take<sm100::BagDev>(nb);
   w.tmaps = c.take<CUtensorMap>(nb);
   // keys and the finalize arrival counters are zeroed together (one memset): keep them adjacent
@@ -429,18 +410,12 @@ static int forward_bags_impl(const dsmil_params_t* p, const float* const* Xs, co
   std::vector<sm100::BagDev> tbl(nb);
   long long row = 0;
   int tile = 0, rec = 0;
-  // inference on the shipped shape: attention pass fused into the phase-1 kernel (one record per (CTA, bag))
+  // inference (Q stays in the tile-blocked workspace) on D <= 512, opt-in: the CTA-pair phase-1 kernel (fwd_pair.cuh)
   const bool pair_path = save_Q == nullptr && save_H1 == nullptr && use_pair(p);
-  int total_tiles = 0;
-  for (int b = 0; b < nb; ++b) total_tiles += static_cast<int>((Ns[b] + sm100::kTileM - 1) / sm100::kTileM);
-  const bool fuse_path = !pair_path && save_Q == nullptr && save_H1 == nullptr && use_fuse(p, total_tiles) &&
-                         l2_budget_bytes() >= (size_t(1) << 40);
-  const int fuse_grid = sm100::qmlp_grid(total_tiles, num_sms());
   for (int b = 0; b < nb; ++b) {
     DSMIL_REQUIRE(Ns[b] >= 1 && Ns[b] < 0xffffffffll && Xs[b], "bag %d: empty or NULL", b);
     DSMIL_REQUIRE((reinterpret_cast<uintptr_t>(Xs[b]) & 15) == 0, "bag %d: features must be 16-byte aligned", b);
-    const int bag_tiles = static_cast<int>((Ns[b] + sm100::kTileM - 1) / sm100::kTileM);
-    const int nrec = fuse_path ? std::min(bag_tiles, fuse_grid) : recs_for_bag(Ns[b]);
+    const int nrec = recs_for_bag(Ns[b]);
     tbl[b] = sm100::BagDev{Xs[b], Ns[b], row, tile, rec, nrec, 0};
     row += Ns[b];
     tile += static_cast<int>((Ns[b] + sm100::kTileM - 1) / sm100::kTileM);
@@ -450,7 +425,6 @@ static int forward_bags_impl(const dsmil_params_t* p, const float* const* Xs, co
   DSMIL_CUDA_OK(cudaMemsetAsync(w.keys, 0, sizeof(unsigned long long) * (kMaxC + 1) * nb, st));
   uint8_t* img = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(w.wimg) + 1023) & ~uintptr_t(1023));
   int rc;
-  // inference (Q stays in the tile-blocked workspace) on D <= 512: the CTA-pair kernel (fwd_pair.cuh)
   if (pair_path) {
     std::vector<CUtensorMap> maps(nb);
     for (int b = 0; b < nb; ++b)
@@ -472,15 +446,6 @@ static int forward_bags_impl(const dsmil_params_t* p, const float* const* Xs, co
       return rc;
     sm100::AttendArgs aa{w.table, 0, nb, 0, D, C, Q, 1, w.keys, A, w.recs, nullptr};
     if ((rc = sm100::launch_attend_b(aa, rec, st))) return rc;
-    sm100::FinalizeArgs fa{w.table, 0, D, C, w.recs, w.keys, p->Wf, p->bf, A, B, pred,
-                           reinterpret_cast<long long*>(crit), w.pred_part, w.counters, nullptr, 0, 0};
-    return sm100::launch_finalize_b(fa, nb, st);
-  }
-  if (fuse_path) {
-    unsigned int* bag_done = w.counters + nb;      // second half of the zeroed counter block
-    if ((rc = sm100::launch_qmlp(p, w.table, 0, nb, 0, tile, classes_in ? nullptr : classes, w.keys, Q, nullptr, img,
-                                 num_sms(), st, 1, A, w.recs, bag_done)))
-      return rc;
     sm100::FinalizeArgs fa{w.table, 0, D, C, w.recs, w.keys, p->Wf, p->bf, A, B, pred,
                            reinterpret_cast<long long*>(crit), w.pred_part, w.counters, nullptr, 0, 0};
     return sm100::launch_finalize_b(fa, nb, st);

@@ -13,7 +13,7 @@ namespace dsmil {
 namespace sm100 {
 
 constexpr int kAttRows = 128;          // rows per attend tile (same tiling as phase 1)
-constexpr int kMaxRecPerBag = 160;         // >= SM count: the fused attention pass emits one record per (CTA, bag)
+constexpr int kMaxRecPerBag = 128;
 
 struct AttendArgs {
   const BagDev* bags;

@@ -18,14 +18,17 @@
 //                          blocks (column-major, coalesced) or row-major when training keeps it
 //   smem (196 KB): W ring 2 x 32 KB | A ring 4 x 32 KB (hi tile + lo tile) | Wi rows
 //   TMEM columns (512): H1 accumulators 2 x 128 | Q accumulator 128 | A2 hi 64 | A2 lo 64
-//   Measured state and what limits it: DESIGN.md section 4.1, profiles/.
+//   Measured state and what limits it: DESIGN.md section 4.1, profiles/.  Round-2 findings (profiles/r2_bench_history.md):
+//   neither ring depth (A 2-4 / W 2-4 stages), nor the load chain in isolation (tools/chainbench: 6.5 TB/s), nor deeper
+//   epilogue unrolling changes the 117 us per 16-bag step; the CTA-0 timeline (tools/ktrace.py) shows the eight epilogue
+//   warps busy ~14 k of the ~20 k cycles of a tile (H1 epilogue 4.2 k, Q epilogue incl. the 64 KB of tile-blocked stores
+//   9.5 k): the epilogue role paces the pipeline.
 #pragma once
 #include <cuda_bf16.h>
 #include <type_traits>
 #include <cstdlib>
 
 #include "common.cuh"
-#include "fwd_kernels.cuh"
 
 namespace dsmil {
 namespace sm100 {
@@ -184,10 +187,6 @@ struct QmlpArgs {
   int q_blocked;          // 1: Q is written in tile blocks (coalesced epilogue stores; inference path)
   int mode;               // timing experiments only (DSMIL_B200_DEBUG_MODE): bit0 no Q stores, bit1 no scores,
                           // bit2 converter skips convert+store, bit3 no MMAs, bit4 epilogue skips math
-  // FUSE instantiations only (attention pass folded into the epilogue warps' idle time, see k_qmlp_sm100):
-  float* A;               // packed [sumN, C]: raw attention logits (normalised by k_finalize_b)
-  float* recs;            // partial records (m | s | Bp), bags[b].rec_off + local index of the CTA's first tile in the bag
-  unsigned int* bag_done; // [nb] tiles of the bag whose scores / keys / Q are complete (zeroed by the host)
 };
 // trace slots: [role][event][index] -> role 0 converter (warp 0 of the role), 1 mma, 2 epilogue
 #define DSMIL_TRACE(role, ev, idx)                                                            \
@@ -248,25 +247,9 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return 1.f - __fdividef(2.f, e + 1.f);
 }
 
-// ---- helpers of the fused attention pass ----
-__device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// L2 eviction policies: phase 1 keeps X resident for the attention pass (which is its last use)
+// L2 eviction policy for cache-hinted loads (the pair kernel keeps X resident for the attention pass)
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol)); return pol;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol)); return pol;
-}
-__device__ __forceinline__ float4 ldg_policy(const float4* p, uint64_t pol) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
-  return v;
 }
 
 // dynamic smem carve (bytes, from a 1024-aligned base)
@@ -277,13 +260,7 @@ constexpr int kSmemFixed = kOffWi;
 
 // CT: classes rounded up to 1/2/4/8.  DT: compile-time feature size (512 = every shipped configuration:
 // the chunk loops unroll and the load offsets become immediates) or 0 = run-time D.
-// FUSE (inference, tile-blocked Q, DT = 512, CT <= 2): the attention pass (dsmil.py:53-57) runs in the EPILOGUE warps
-// between their phase-1 duties: as soon as every tile of a bag has gone through phase 1 (per-bag arrival counter) they
-// re-read the CTA's own tiles of that bag from L2 (X was loaded with an evict-last policy, Q was written a few
-// microseconds earlier), take L = Q.q_max / sqrt(128), e = exp(L - Lb) with the a-priori bound Lb = |q_max|_1 / sqrt(128)
-// (|Q| <= 1 after tanh: no running max, partial sums are plain sums) and accumulate e^T X for the bag in registers; one
-// record (Lb, sum e, Bp) per (CTA, bag) goes to k_finalize_b.  X is read from HBM once; no separate attend kernel.
-template <int CT, int DT, bool FUSE = false>
+template <int CT, int DT>
 __global__ void __launch_bounds__(kThreads, 1)
 k_qmlp_sm100(const QmlpArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -293,11 +270,6 @@ k_qmlp_sm100(const QmlpArgs a) {
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) float s_b1[kQ], s_b2[kQ];
   __shared__ BagDev s_bags[kSmemBags];           // the launch's slice of the bag table (tile-boundary lookups)
-  __shared__ __align__(16) float s_qm[FUSE ? CT : 1][FUSE ? kQ : 1];        // q_max of the bag being attended
-  __shared__ __align__(16) float s_e[FUSE ? kTileM : 1][FUSE ? CT : 1];     // exp weights of the tile being attended
-  __shared__ __align__(16) float s_fold[FUSE ? CT * (DT ? DT : 1) : 1];     // fold of the two row parities at a flush
-  __shared__ float s_lb[CT], s_red[4][CT];
-  __shared__ int s_flag;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = DT ? DT : a.D, C = a.C;
@@ -370,17 +342,15 @@ k_qmlp_sm100(const QmlpArgs a) {
       ld_full = ld_row - r0 + kTileM <= ld_N;
       xrow = reinterpret_cast<const float4*>(bp->X + static_cast<long long>(ld_row) * D) + seg;
     };
-    const uint64_t pol_keep = FUSE ? l2_policy_evict_last() : 0ull;   // FUSE: X is re-read from L2 by the attention pass
-    auto ldx = [&](const float4* src) { return FUSE ? ldg_policy(src, pol_keep) : ldg_stream(src); };
     auto load_chunk = [&](int kc, float4* dst) {
       if (ld_full) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = ldx(xrow + static_cast<long long>(i) * (8ll * D) + kc * (kChunkK / 4));
+        for (int i = 0; i < 4; ++i) dst[i] = ldg_stream(xrow + static_cast<long long>(i) * (8ll * D) + kc * (kChunkK / 4));
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4* src = xrow + static_cast<long long>(i) * (8ll * D) + kc * (kChunkK / 4);   // 32 rows apart
-          dst[i] = (ld_row + 32 * i < ld_N) ? ldx(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+          dst[i] = (ld_row + 32 * i < ld_N) ? ldg_stream(src) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     };
@@ -615,157 +585,6 @@ k_qmlp_sm100(const QmlpArgs a) {
     long long prev_grow = 0;
     bool prev_live = false;
     TileCursor cur_bag(tbl, 0, a.nb);
-    // ---------------- fused attention pass (FUSE): state of the bag whose tiles are being attended ----------------
-    TileCursor cur_att(tbl, 0, a.nb);
-    int att_i = 0, att_bag = -1, att_slot = 0, prev_bag = 0;
-    float att_acc[CT][4], att_s[CT];
-#pragma unroll
-    for (int k = 0; k < CT; ++k) { att_s[k] = 0.f; att_acc[k][0] = att_acc[k][1] = att_acc[k][2] = att_acc[k][3] = 0.f; }
-    const uint64_t pol_last_use = FUSE ? l2_policy_evict_first() : 0ull;
-    // one record (Lb, sum e, Bp) for the finished bag: fold the two row parities in a fixed order
-    auto att_flush = [&]() {
-      const BagDev bg = tbl[att_bag];
-      float* rec = a.recs + static_cast<size_t>(bg.rec_off + att_slot) * rec_floats(a.C, DT);
-      const int half = tid >> 7, c4 = tid & 127;
-#pragma unroll
-      for (int k = 0; k < CT; ++k) {
-        const float v = warp_sum(att_s[k]);                      // rows live in threads 0..127 (warps 0..3)
-        if (lane == 0 && warp < 4) s_red[warp][k] = v;
-      }
-      if (half == 1) {
-#pragma unroll
-        for (int k = 0; k < CT; ++k)
-          *reinterpret_cast<float4*>(&s_fold[k * DT + c4 * 4]) = make_float4(att_acc[k][0], att_acc[k][1], att_acc[k][2], att_acc[k][3]);
-      }
-      bar_epi();
-      if (half == 0) {
-#pragma unroll
-        for (int k = 0; k < CT; ++k)
-          if (k < a.C) {
-            const float4 o = *reinterpret_cast<const float4*>(&s_fold[k * DT + c4 * 4]);
-            float* dst = rec + 2 * a.C + static_cast<size_t>(k) * DT + c4 * 4;
-            dst[0] = att_acc[k][0] + o.x; dst[1] = att_acc[k][1] + o.y; dst[2] = att_acc[k][2] + o.z; dst[3] = att_acc[k][3] + o.w;
-          }
-      }
-      if (tid < a.C) {
-        rec[tid] = s_lb[tid];
-        rec[a.C + tid] = ((s_red[0][tid] + s_red[1][tid]) + s_red[2][tid]) + s_red[3][tid];
-      }
-      bar_epi();
-#pragma unroll
-      for (int k = 0; k < CT; ++k) { att_s[k] = 0.f; att_acc[k][0] = att_acc[k][1] = att_acc[k][2] = att_acc[k][3] = 0.f; }
-    };
-    // attend the CTA's own tile number att_i if its bag is complete (or wait for it when `must`); returns false if not ready
-    auto att_try = [&](bool must) -> bool {
-      const int utile = a.tile0 + blockIdx.x + att_i * static_cast<int>(gridDim.x);
-      cur_att.seek(utile);
-      const int bag = cur_att.bag;
-      const BagDev bg = tbl[bag];
-      const int bag_tiles = static_cast<int>((bg.N + kTileM - 1) / kTileM);
-      if (tid == 0) {
-        unsigned int done = ld_acquire_u32(a.bag_done + a.bag0 + bag);
-        uint32_t spins = 0;
-        while (must && done != static_cast<unsigned int>(bag_tiles)) {
-          __nanosleep(256);
-          done = ld_acquire_u32(a.bag_done + a.bag0 + bag);
-          if (++spins > (1u << 24)) __trap();
-        }
-        s_flag = done == static_cast<unsigned int>(bag_tiles);
-      }
-      bar_epi();
-      const bool ready = s_flag != 0;
-      bar_epi();                                   // s_flag may be rewritten by the next attempt
-      if (!ready) return false;
-      if (bag != att_bag) {
-        if (att_bag >= 0) att_flush();
-        att_bag = bag;
-        att_slot = utile - bg.tile_off;            // local index of this CTA's first tile in the bag -> record slot
-        // q_max = Q rows of the critical instances (dsmil.py:53-54), gathered from the tile-blocked Q (L2)
-        for (int i = tid; i < CT * kQ; i += 256) {
-          const int k = i / kQ, jq = i % kQ;
-          float v = 0.f;
-          if (k < a.C) {
-            const uint32_t row = key_row(__ldcg(a.keys + static_cast<size_t>(a.bag0 + bag) * kMaxC + k));
-            v = __ldcg(a.Q + static_cast<size_t>(bg.tile_off + row / kTileM) * (kTileM * kQ) + jq * kTileM + (row % kTileM));
-          }
-          s_qm[k][jq] = v;
-        }
-        bar_epi();
-        if (warp < CT) {                           // a-priori logit bound: |Q| <= 1  =>  |L| <= |q_max|_1 / sqrt(128)
-          const float4 q4 = *reinterpret_cast<const float4*>(&s_qm[warp][lane * 4]);
-          const float sabs = warp_sum((fabsf(q4.x) + fabsf(q4.y)) + (fabsf(q4.z) + fabsf(q4.w)));
-          if (lane == 0) s_lb[warp] = __fdiv_rn(sabs, kScale);
-        }
-        bar_epi();
-      }
-      const int t = utile - bg.tile_off;
-      const long long r0 = static_cast<long long>(t) * kTileM;
-      const int rows = static_cast<int>((bg.N - r0) < kTileM ? (bg.N - r0) : kTileM);
-      {   // logits: thread (row r, column half hf) reads 64 coalesced columns of the tile-blocked Q
-        const int r = tid & 127, hf = tid >> 7;
-        const float* qb = a.Q + static_cast<size_t>(utile) * (kTileM * kQ) + static_cast<size_t>(hf * 64) * kTileM + r;
-        float d[CT];
-#pragma unroll
-        for (int k = 0; k < CT; ++k) d[k] = 0.f;
-#pragma unroll 4
-        for (int c = 0; c < 64; c += 4) {
-          const float q0 = __ldcg(qb + (c + 0) * kTileM), q1 = __ldcg(qb + (c + 1) * kTileM);
-          const float q2 = __ldcg(qb + (c + 2) * kTileM), q3 = __ldcg(qb + (c + 3) * kTileM);
-#pragma unroll
-          for (int k = 0; k < CT; ++k) {
-            const float4 w = *reinterpret_cast<const float4*>(&s_qm[k][hf * 64 + c]);
-            d[k] = fmaf(q0, w.x, d[k]); d[k] = fmaf(q1, w.y, d[k]); d[k] = fmaf(q2, w.z, d[k]); d[k] = fmaf(q3, w.w, d[k]);
-          }
-        }
-        if (hf == 1) {
-#pragma unroll
-          for (int k = 0; k < CT; ++k) s_e[r][k] = d[k];            // park the upper-half partial
-        }
-        bar_epi();
-        float ev[CT];
-#pragma unroll
-        for (int k = 0; k < CT; ++k) ev[k] = 0.f;
-        if (hf == 0) {
-#pragma unroll
-          for (int k = 0; k < CT; ++k) {
-            const float L = __fdiv_rn(d[k] + s_e[r][k], kScale);     // dsmil.py:56: a division by sqrt(128f)
-            if (r < rows) {
-              if (k < a.C) a.A[(bg.row_off + r0 + r) * a.C + k] = L;
-              ev[k] = expf(L - s_lb[k]);
-              att_s[k] += ev[k];
-            }
-          }
-        }
-        bar_epi();                                   // parked partials consumed
-        if (hf == 0) {
-#pragma unroll
-          for (int k = 0; k < CT; ++k) s_e[r][k] = ev[k];
-        }
-        bar_epi();
-      }
-      {   // weighted feature sum: this thread takes rows of its parity, float4 column c4 (D = 512 = 128 float4)
-        const int half = tid >> 7, c4 = tid & 127;
-        const float4* xb = reinterpret_cast<const float4*>(bg.X + r0 * DT) + c4;
-#pragma unroll 8
-        for (int r = half; r < rows; r += 2) {
-          const float4 x = ldg_policy(xb + static_cast<long long>(r) * (DT / 4), pol_last_use);
-#pragma unroll
-          for (int k = 0; k < CT; ++k) {
-            const float e = s_e[r][k];
-            att_acc[k][0] = fmaf(e, x.x, att_acc[k][0]); att_acc[k][1] = fmaf(e, x.y, att_acc[k][1]);
-            att_acc[k][2] = fmaf(e, x.z, att_acc[k][2]); att_acc[k][3] = fmaf(e, x.w, att_acc[k][3]);
-          }
-        }
-      }
-      bar_epi();                                     // s_e free for the next tile
-      ++att_i;
-      return true;
-    };
-    // scores, keys and Q of `tile` are complete: count it for its bag (release: barrier, then one fence + atomic)
-    auto publish_tile = [&](int bag) {
-      bar_epi();
-      if (tid == 0) { __threadfence(); atomicAdd(a.bag_done + a.bag0 + bag, 1u); }
-    };
     for (int tile = a.tile0 + blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
       cur_bag.seek(tile);
       const BagDev bg = tbl[cur_bag.bag];
@@ -817,27 +636,13 @@ k_qmlp_sm100(const QmlpArgs a) {
       mbar_arrive(bar(H1_EMPTY + b));
       mbar_arrive(bar(A2_FULL));
       if (tid == 0) DSMIL_TRACE(2, 1, it);
-      if (it > 0) {
-        q_epilogue(it - 1, prev_grow, prev_live, prev_tile);
-        if constexpr (FUSE) {
-          publish_tile(prev_bag);
-          if (att_i < it) att_try(false);            // at most one attended tile per phase-1 tile: the epilogue stays responsive
-        }
-      }
+      if (it > 0) q_epilogue(it - 1, prev_grow, prev_live, prev_tile);
       if (tid == 0) DSMIL_TRACE(2, 2, it);
       prev_grow = grow;
       prev_live = live;
       prev_tile = tile;
-      prev_bag = cur_bag.bag;
     }
-    if (it > 0) {
-      q_epilogue(it - 1, prev_grow, prev_live, prev_tile);
-      if constexpr (FUSE) {
-        publish_tile(prev_bag);
-        while (att_i < it) att_try(true);            // drain: the remaining bags complete as the other CTAs finish
-        if (att_bag >= 0) att_flush();
-      }
-    }
+    if (it > 0) q_epilogue(it - 1, prev_grow, prev_live, prev_tile);
   }
   tc_fence_before();
   __syncthreads();
@@ -885,20 +690,15 @@ inline int launch_prep_wimg(const dsmil_params_t* p, uint8_t* wimg, cudaStream_t
 
 // scores + arg-max keys + Q (+H1) for the tiles [tile0, tile0+ntiles) of bags [bag0, bag0+nb).
 // wimg must already hold the images (launch_prep_wimg).
-// fused attention (FUSE instantiations): D == 512, C <= 2, tile-blocked Q, scores computed here
-inline bool qmlp_fuse_supported(const dsmil_params_t* p) { return qmlp_supported(p) && p->D == 512 && p->C <= 2 && !p->passing_v; }
-inline int qmlp_grid(int ntiles, int num_sms) { return ntiles < num_sms ? ntiles : num_sms; }
-
 inline int launch_qmlp(const dsmil_params_t* p, const BagDev* bags_dev, int bag0, int nb, int tile0, int ntiles,
                        float* classes, unsigned long long* keys, float* Q, float* H1, const uint8_t* wimg,
-                       int num_sms, cudaStream_t st, int q_blocked = 0, float* fuse_A = nullptr, float* fuse_recs = nullptr,
-                       unsigned int* fuse_bag_done = nullptr) {
+                       int num_sms, cudaStream_t st, int q_blocked = 0) {
   const int D = p->D, C = p->C;
   const uint8_t* w2img = wimg + static_cast<size_t>(D / kChunkK) * kChunkBytes;
   QmlpArgs a{bags_dev, bag0, nb, tile0, ntiles, D, C, p->Wi, p->bi, p->b1, p->b2, wimg, w2img, classes, keys, Q, H1,
-             g_trace_buf, q_blocked, debug_mode(), fuse_A, fuse_recs, fuse_bag_done};
+             g_trace_buf, q_blocked, debug_mode()};
   const size_t smem = qmlp_smem_bytes(C, D);
-  const int grid = qmlp_grid(ntiles, num_sms);
+  const int grid = ntiles < num_sms ? ntiles : num_sms;
   auto go = [&](auto kern) -> int {
     // (set on every launch: the instantiations share one function-pointer TYPE, so a cached flag here would be
     //  shared between them -- found by the D=1024 / C=1 shape tests; the call costs ~1 us of host time)
@@ -909,10 +709,6 @@ inline int launch_qmlp(const dsmil_params_t* p, const BagDev* bags_dev, int bag0
     DSMIL_LAUNCH_OK("k_qmlp_sm100");
     return 0;
   };
-  if (fuse_A != nullptr) {   // caller checked qmlp_fuse_supported(p) and q_blocked
-    if (C == 1) return go(k_qmlp_sm100<1, 512, true>);
-    return go(k_qmlp_sm100<2, 512, true>);
-  }
   if (D == 512) {
     if (C == 1) return go(k_qmlp_sm100<1, 512>);
     if (C == 2) return go(k_qmlp_sm100<2, 512>);
