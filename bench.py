@@ -342,7 +342,47 @@ def run_extras(args, p, net, bags, dev, ms_per_step):
     if refmod is not None:
         msr = cuda_time_ms(make_train(refmod), 10, warm=3)
         ex["train_n15000_c1"].update({"torch_eager_gpu_ms": msr, "speedup": msr / mst})
+    # (5) the embedder of compute_feats.py:146-174: torchvision ResNet-18 with InstanceNorm2d + fc, batch 128 x 3 x 224 x 224
+    try:
+        ex["embed_resnet18_in"] = embed_leg(dev, refmod)
+    except Exception as e:                                    # torchvision missing etc.: report, do not fail the bench
+        ex["embed_resnet18_in"] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
     return ex
+
+
+def make_embedder(modlib, dev, fuse):
+    import torchvision.models as models
+    torch.manual_seed(0)
+    resnet = models.resnet18(weights=None, norm_layer=torch.nn.InstanceNorm2d)    # compute_feats.py:154 (norm_layer='instance')
+    for prm in resnet.parameters():
+        prm.requires_grad = False
+    resnet.fc = torch.nn.Identity()
+    ic = modlib.IClassifier(resnet, 512, C).to(dev).eval()
+    if fuse:
+        from dsmil_wsi_b200.embedder import fuse_instance_norm
+        fuse_instance_norm(ic.feature_extractor)
+    return ic
+
+
+def embed_leg(dev, refmod, batch=128):
+    import dsmil as mil
+    g = torch.Generator(device=dev).manual_seed(3)
+    x = torch.rand(batch, 3, 224, 224, generator=g, device=dev)
+    out = {"batch": batch, "what": "IClassifier(ResNet-18 with nn.InstanceNorm2d, fc) on a 128 x 3 x 224 x 224 fp32 batch "
+                                   "(compute_feats.py:70-76,146-174); convolutions = cuDNN in both arms (TF32 allowed, torch default)"}
+    ours = make_embedder(mil, dev, True)
+    with torch.no_grad():
+        ms = cuda_time_ms(lambda: ours(x), 5, warm=2)
+    out.update({"value": batch / (ms / 1e3), "unit": "patches/s", "ms_per_batch": ms,
+                "ours": "convs cuDNN; InstanceNorm + residual + ReLU fused (dsmil_instnorm_act); fc scores by libdsmil_b200"})
+    if refmod is not None:
+        ref = make_embedder(refmod, dev, False)
+        with torch.no_grad():
+            msr = cuda_time_ms(lambda: ref(x), 5, warm=2)
+            fa, fb = ours(x)[0], ref(x)[0]
+        out.update({"torch_eager_gpu_ms": msr, "torch_eager_gpu_patches_per_s": batch / (msr / 1e3), "speedup": msr / ms,
+                    "max_abs_feature_diff": float((fa - fb).abs().max())})
+    return out
 
 
 def run_ours(args):
@@ -583,6 +623,45 @@ def run_ours(args):
                   "step_launch": "CUDA graph replay" if gplan is not None else "eager"}
         del giant
 
+    # ---- BASELINE configs[3]: ResNet-18 embedding of 224x224 patches + aggregator, patches sharded over the ranks ----
+    embed_agg = None
+    if not args.no_extras:
+        try:
+            import dsmil as mil
+            from dsmil_wsi_b200.sharded import sharded_forward
+            PB, NBATCH = 128, 4                       # 512 patches per rank per slide
+            ic = make_embedder(mil, dev, True)
+            gen = torch.Generator(device=dev).manual_seed(50 + rank)
+            px = [torch.rand(PB, 3, 224, 224, generator=gen, device=dev) for _ in range(NBATCH)]
+            sops = CudaShardOps(milnet_params(net)) if world > 1 else None
+
+            def slide():
+                with torch.no_grad():
+                    feats = torch.cat([ic(b)[0] for b in px])             # [512, 512] on this rank
+                    if world == 1:
+                        return net(feats)
+                    return sharded_forward(sops, feats, rank * PB * NBATCH)
+            for _ in range(2):
+                slide()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(3):
+                slide()
+            s1.record()
+            barrier()
+            tms = torch.tensor([s0.elapsed_time(s1) / 3], device=dev)
+            if world > 1:
+                dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            tms = float(tms.item())
+            embed_agg = {"value": PB * NBATCH * world / (tms / 1e3), "unit": "patches/s", "ms_per_slide": tms,
+                         "slides_per_s": 1e3 / tms, "patches_per_rank": PB * NBATCH, "n_gpus": world, "scaling": "weak",
+                         "what": "per slide: each rank embeds its 512 patches (ResNet-18-InstanceNorm, fused norm kernel) and the "
+                                 "features go straight into the row-sharded DSMIL aggregator (NCCL: candidates + partial sums)"}
+            del px, ic
+        except Exception as e:
+            embed_agg = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+
     # ---- per-phase breakdown of one host-launched sharded step (CUDA events on the launch stream, max over ranks) -----
     breakdown = None
     if world > 1 and bops is not None and not args.no_extras:
@@ -654,7 +733,7 @@ def run_ours(args):
                           "forward_path": int(lib.dsmil_forward_path(ctypes.byref(_lib.DsmilParams(D, C, 1, 0)), NBAG))},
                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches * world,
                "clocks": clocks, "strong_n100k": strong, "parity_check": parity, "step_breakdown": breakdown,
-               "extras": extras}
+               "embed_aggregate_resnet18": embed_agg, "extras": extras}
         print(json.dumps(out))
     if world > 1:
         # CUDA graphs that captured NCCL collectives keep communicator resources alive; tearing the process group down

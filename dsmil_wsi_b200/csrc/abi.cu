@@ -16,6 +16,7 @@
 #include "fwd_sm100.cuh"
 #include "fwd_batched.cuh"
 #include "fwd_pair.cuh"
+#include "embed_kernels.cuh"
 
 namespace dsmil {
 
@@ -555,6 +556,15 @@ int dsmil_patches_u8_to_f32(const uint8_t* in, int64_t B, int32_t H, int32_t W, 
   k_u8hwc_to_f32chw<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, B, H, W, Cc, out);
   DSMIL_LAUNCH_OK("k_u8hwc_to_f32chw");
   return 0;
+}
+
+int dsmil_instnorm_act(const float* x, const float* residual, float* y, int64_t planes, int32_t HW, float eps,
+                       int32_t relu, void* stream) {
+  DSMIL_REQUIRE(planes >= 0 && HW >= 1 && HW <= kInPlaneMax && eps >= 0.f && (planes == 0 || (x && y)),
+                "bad arguments (HW must be in [1, %d])", kInPlaneMax);
+  DSMIL_REQUIRE(planes < (1ll << 31), "too many planes");
+  if (planes == 0) return 0;
+  return launch_instnorm(x, residual, y, planes, HW, eps, relu, static_cast<cudaStream_t>(stream));
 }
 
 int dsmil_profile_enable(int on) {

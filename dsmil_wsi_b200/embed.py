@@ -137,6 +137,10 @@ def embed_bag(paths: Sequence[str], i_classifier, batch_size: int = 128, num_wor
     if not paths:
         return None, None
     i_classifier.eval()
+    fe = getattr(i_classifier, "feature_extractor", None)
+    if fe is not None and os.environ.get("DSMIL_B200_FUSE_IN", "1") != "0":
+        from .embedder import fuse_instance_norm            # InstanceNorm + residual + ReLU of the backbone: one kernel each
+        fuse_instance_norm(fe)                               # (idempotent; leaves parameters / state_dict untouched)
     first = _decode_u8(paths[0])
     H, W = first.shape[:2]
     feats_out, cls_out = [], []

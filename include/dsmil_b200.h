@@ -82,6 +82,15 @@ int dsmil_gather_rows(const float* X, int64_t N, int32_t D, const int64_t* idx, 
  * .float().cuda()): uint8 HWC patches [B,H,W,Cc] (device) -> float32 CHW [B,Cc,H,W] = value / 255. */
 int dsmil_patches_u8_to_f32(const uint8_t* in, int64_t B, int32_t H, int32_t W, int32_t Cc, float* out, void* stream);
 
+/* Backbone of the embedding loop (compute_feats.py:146-170 builds a torchvision ResNet with norm_layer =
+ * nn.InstanceNorm2d, dsmil.py:21-25 runs it): after every convolution the reference executes instance_norm ->
+ * (+ identity) -> relu as separate passes.  One pass here:  y = [relu]( instance_norm(x) [+ residual] )  over
+ * `planes` = N*C planes of HW contiguous fp32 elements (NCHW), biased variance, eps as given, no affine parameters and
+ * no running statistics (the nn.InstanceNorm2d defaults the reference uses).  residual may be NULL; y == x is allowed.
+ * HW <= 16384. */
+int dsmil_instnorm_act(const float* x, const float* residual, float* y, int64_t planes, int32_t HW, float eps,
+                       int32_t relu, void* stream);
+
 /* Live per-kernel timing for the roofline report (bench.py): when enabled, tagged launches are
  * bracketed by CUDA events on the launching stream.  dsmil_profile_read synchronises those events,
  * returns summed milliseconds and launch counts per tag (arrays of 8: 0 scores, 1 q-mlp, 2 attend,
