@@ -10,8 +10,10 @@
  *              sign, NaN is the empty field pandas writes, inf is "inf".  Done in integer arithmetic
  *              (m * 10^4 / 2^s with the remainder inspected), snprintf only for |v| >= 2^39.
  *   reader  -- float32(correctly rounded double of the decimal string) for fields of up to 18 significant digits
- *              without exponent (K / 10^frac with K exact in a double: one IEEE division, which is also what
- *              pandas' C parser does for such fields); anything else goes through strtod.  Empty field = NaN.
+ *              without exponent (K / 10^frac with K exact in a double: one IEEE division = the correctly rounded
+ *              value, i.e. Python's float()); anything else goes through strtod.  Empty field = NaN.  For the '%.4f'
+ *              wire format this is bit-identical to the reference's pd.read_csv route (pinned on the committed
+ *              fixtures); for other fraction lengths pandas' own parser may differ from float() by one ulp.
  */
 #include <math.h>
 #include <stdint.h>

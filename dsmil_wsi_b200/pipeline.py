@@ -42,7 +42,10 @@ class HostBagPipeline:
     @torch.no_grad()
     def run(self, host_bags: Sequence[torch.Tensor]):
         """host_bags: CPU fp32 [N_i, D] tensors (pinned for full overlap).  Returns per bag
-        (classes, prediction_bag, A, B) as HOST tensors; synchronises once at the end."""
+        (classes, prediction_bag, A, B) as HOST tensors; synchronises once at the end.
+
+        The returned tensors are VIEWS of this pipeline's pinned result buffers, which the next `run()` overwrites
+        (asynchronously): consume or `.clone()` them before calling `run()` again."""
         results = []
         with torch.cuda.device(self.dev):
             compute = torch.cuda.current_stream()
