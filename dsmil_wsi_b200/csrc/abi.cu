@@ -187,6 +187,12 @@ static bool stream_is_capturing(cudaStream_t st) {
   return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
 }
 
+// tile-blocked Q holds the pre-activation, tanh applied by its readers (DSMIL_B200_QPRE=0: r1 behaviour, tanh in phase 1)
+static int blocked_q_mode() {
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("DSMIL_B200_QPRE"); mode = (e && e[0] == '0') ? 1 : 2; }
+  return mode;
+}
 static bool use_pair(const dsmil_params_t* p) {
   // CTA-pair phase 1 (fwd_pair.cuh): parity-green, but not yet faster than k_qmlp_sm100 (profiles/r2_bench_history.md),
   // so it is opt-in: DSMIL_B200_PAIR=1
@@ -467,7 +473,7 @@ static int forward_bags_impl(const dsmil_params_t* p, const float* const* Xs, co
     const int t1 = (b1 < nb) ? tbl[b1].tile_off : tile;
     const int r0 = tbl[b0].rec_off;
     const int r1 = (b1 < nb) ? tbl[b1].rec_off : rec;
-    const int q_blocked = save_Q ? 0 : 1;   // training keeps Q row-major for the backward kernels
+    const int q_blocked = save_Q ? 0 : blocked_q_mode();   // training keeps Q (after tanh) row-major for the backward kernels
     if ((rc = sm100::launch_qmlp(p, w.table, b0, b1 - b0, t0, t1 - t0, classes_in ? nullptr : classes, w.keys, Q,
                                  save_H1, img, num_sms(), st, q_blocked)))
       return rc;
@@ -1010,9 +1016,10 @@ int dsmil_shard_bags_phase1(const dsmil_params_t* p, const float* const* Xs, con
   uint8_t* img = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(w.base.wimg) + 1023) & ~uintptr_t(1023));
   // (a captured serving loop also reuses the weight images of the preceding eager call: re-capture after a weight update)
   if (!stream_is_capturing(st) && (rc = sm100::launch_prep_wimg(p, img, st))) return rc;
-  if ((rc = sm100::launch_qmlp(p, w.base.table, 0, nb, 0, tiles, classes, w.base.keys, w.base.Q, nullptr, img, num_sms(), st, 1)))
+  if ((rc = sm100::launch_qmlp(p, w.base.table, 0, nb, 0, tiles, classes, w.base.keys, w.base.Q, nullptr, img, num_sms(), st,
+                               blocked_q_mode())))
     return rc;
-  sm100::k_gather_cand_b<<<dim3(p->C, nb), kQ, 0, st>>>(w.base.table, w.base.keys, classes, w.base.Q, 1, w.row_offsets, p->C,
+  sm100::k_gather_cand_b<<<dim3(p->C, nb), kQ, 0, st>>>(w.base.table, w.base.keys, classes, w.base.Q, blocked_q_mode(), w.row_offsets, p->C,
                                                         cand_recs);
   DSMIL_LAUNCH_OK("k_gather_cand_b");
   return 0;
@@ -1033,7 +1040,7 @@ int dsmil_shard_bags_phase2(const dsmil_params_t* p, const float* const* Xs, con
   if ((rc = build_table(Xs, Ns, nb, tbl, &tiles, &recs))) return rc;   // the device table was written by phase 1
   sm100::k_merge_cand_b<<<dim3(p->C, nb), kQ, 0, st>>>(cands_all, G, nb, p->C, w.qmax, reinterpret_cast<long long*>(crit_idx));
   DSMIL_LAUNCH_OK("k_merge_cand_b");
-  sm100::AttendArgs aa{w.base.table, 0, nb, 0, p->D, p->C, w.base.Q, 1, w.base.keys, A, w.base.recs, w.qmax};
+  sm100::AttendArgs aa{w.base.table, 0, nb, 0, p->D, p->C, w.base.Q, blocked_q_mode(), w.base.keys, A, w.base.recs, w.qmax};
   if ((rc = sm100::launch_attend_b(aa, recs, st))) return rc;
   sm100::FinalizeArgs fa{w.base.table, 0, p->D, p->C, w.base.recs, w.base.keys, p->Wf, p->bf, A, nullptr, nullptr, nullptr,
                          w.base.pred_part, w.base.counters, recs_out, 0, 0};

@@ -21,7 +21,7 @@ struct AttendArgs {
   int rec0;                 // first record index covered by this launch (== blockIdx.x 0)
   int D, C;
   const float* Q;           // packed [sumN,128] row-major, or tile-blocked column-major (q_blocked)
-  int q_blocked;
+  int q_blocked;            // 0 row-major Q; 1 tile blocks of Q; 2 tile blocks of the pre-activation (tanh applied on read)
   const unsigned long long* keys;  // [nbags][kMaxC]
   float* A;                 // packed [sumN,C]: receives the raw logits here
   float* recs;              // [total records][rec_floats(C,D)]
@@ -60,6 +60,7 @@ k_attend_b(const AttendArgs a) {
       const long long row = key_row(a.keys[static_cast<size_t>(bag) * kMaxC + k]);
       v = a.q_blocked ? a.Q[static_cast<size_t>(bg.tile_off + row / kAttRows) * (kAttRows * kQ) + j * kAttRows + (row % kAttRows)]
                       : a.Q[(bg.row_off + row) * kQ + j];
+      if (a.q_blocked == 2) v = fast_tanh2(f2{v, 0.f}).x;
     }
     sq[k][j] = v;
   }
@@ -93,8 +94,12 @@ k_attend_b(const AttendArgs a) {
       for (int k = 0; k < CT; ++k) d[k] = 0.f;
 #pragma unroll 4
       for (int c = 0; c < 64; c += 4) {
-        const float q0 = __ldg(qb + (c + 0) * kAttRows), q1 = __ldg(qb + (c + 1) * kAttRows);
-        const float q2 = __ldg(qb + (c + 2) * kAttRows), q3 = __ldg(qb + (c + 3) * kAttRows);
+        float q0 = __ldg(qb + (c + 0) * kAttRows), q1 = __ldg(qb + (c + 1) * kAttRows);
+        float q2 = __ldg(qb + (c + 2) * kAttRows), q3 = __ldg(qb + (c + 3) * kAttRows);
+        if (a.q_blocked == 2) {                         // the tanh of dsmil.py:31, deferred from the phase-1 epilogue
+          const f2 ta = fast_tanh2(f2{q0, q1}), tb = fast_tanh2(f2{q2, q3});
+          q0 = ta.x; q1 = ta.y; q2 = tb.x; q3 = tb.y;
+        }
 #pragma unroll
         for (int k = 0; k < CT; ++k) {
           const float4 w = *reinterpret_cast<const float4*>(&sq[k][hf * 64 + c]);
@@ -409,9 +414,11 @@ k_gather_cand_b(const BagDev* __restrict__ bags, const unsigned long long* __res
     idx[k] = row + row_offsets[bag];
     score[k] = classes[(bg.row_off + row) * C + k];
   }
-  qrow[threadIdx.x] = q_blocked
+  float qv = q_blocked
       ? Q[static_cast<size_t>(bg.tile_off + row / kAttRows) * (kAttRows * kQ) + threadIdx.x * kAttRows + (row % kAttRows)]
       : Q[(bg.row_off + row) * kQ + threadIdx.x];
+  if (q_blocked == 2) qv = fast_tanh2(f2{qv, 0.f}).x;
+  qrow[threadIdx.x] = qv;
 }
 
 // Winner per (bag, class) over the G ranks' candidate records cands[g][bag]; grid = (C, nb), 128 threads.

@@ -184,7 +184,9 @@ struct QmlpArgs {
   float* Q;               // packed row-major [sumN,128], or (q_blocked) per-tile column-major blocks [tile][128 col][128 row]
   float* H1;              // packed [sumN,128] or NULL
   long long* dbg;         // optional timeline of CTA 0 (clock64 stamps), see DSMIL_B200_TRACE in abi.cu
-  int q_blocked;          // 1: Q is written in tile blocks (coalesced epilogue stores; inference path)
+  int q_blocked;          // 1: Q is written in tile blocks (coalesced epilogue stores; inference path); 2: tile blocks of the
+                          // PRE-activation z2 = acc + b2 -- the tanh moves to the readers of Q (k_attend_b, k_gather_cand_b):
+                          // the epilogue role paces this kernel (profiles/r2_ktrace_old.txt), its readers have idle issue slots
   int mode;               // timing experiments only (DSMIL_B200_DEBUG_MODE): bit0 no Q stores, bit1 no scores,
                           // bit2 converter skips convert+store, bit3 no MMAs, bit4 epilogue skips math
 };
@@ -561,8 +563,9 @@ k_qmlp_sm100(const QmlpArgs a) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 bb = *reinterpret_cast<const float4*>(&s_b2[c0 + 4 * q]);
-            const f2 t0 = fast_tanh2(add2(f2{__uint_as_float(v[4 * q + 0]), __uint_as_float(v[4 * q + 1])}, f2{bb.x, bb.y}));
-            const f2 t1 = fast_tanh2(add2(f2{__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])}, f2{bb.z, bb.w}));
+            f2 t0 = add2(f2{__uint_as_float(v[4 * q + 0]), __uint_as_float(v[4 * q + 1])}, f2{bb.x, bb.y});
+            f2 t1 = add2(f2{__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])}, f2{bb.z, bb.w});
+            if (a.q_blocked == 1) { t0 = fast_tanh2(t0); t1 = fast_tanh2(t1); }
             dst[(4 * q + 0) * kTileM] = t0.x;
             dst[(4 * q + 1) * kTileM] = t0.y;
             dst[(4 * q + 2) * kTileM] = t1.x;
