@@ -759,7 +759,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="multi-GPU: host-launched step instead of the CUDA-graph replay")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra workloads (eager-GPU baseline, N=8192, "
                     "N=15000 training step, N=100k strong scaling, multi-rank parity check)")
-    ap.add_argument("--giant-bags", type=int, default=16, help="N=100 000 bags per step of the strong-scaling workload")
+    ap.add_argument("--giant-bags", type=int, default=32, help="N=100 000 bags per step of the strong-scaling workload")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

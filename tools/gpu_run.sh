@@ -1,16 +1,11 @@
 mkdir -p gpurun_out
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29561 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/r2_bench_8gpu_final.json 2> gpurun_out/r2_bench_8gpu_final.err; echo "bench8 rc=$?"
+timeout 400 python bench.py --cpu-seconds 3 > gpurun_out/r2_bench_1gpu_final2.json 2> gpurun_out/r2_bench_1gpu_final2.err; echo "bench1 rc=$?"
 python - <<'PY'
-import time, torch, sys
-sys.path.insert(0,'.')
-from bench import Weights, make_net, NBAG, D, C
-from dsmil_wsi_b200.pipeline import HostBagPipeline
-dev=torch.device('cuda',0); net=make_net(Weights(0),dev)
-host=[torch.rand(NBAG,D).pin_memory() for _ in range(16)]
-for cs,depth in ((1,2),(2,4),(2,6),(3,6)):
-    pipe=HostBagPipeline(net,NBAG,D,C,depth=depth,copy_streams=cs)
-    for _ in range(2): pipe.run(host)
-    torch.cuda.synchronize(); t0=time.perf_counter()
-    for _ in range(8): pipe.run(host)
-    torch.cuda.synchronize(); dt=(time.perf_counter()-t0)/8
-    print(f"copy_streams={cs} depth={depth}: {dt*1e3:.3f} ms/step  {16*NBAG/dt/1e6:.2f} M patches/s  H2D {16*NBAG*D*4/dt/1e9:.1f} GB/s")
+import json
+for f in ('r2_bench_8gpu_final','r2_bench_1gpu_final2'):
+    try:
+        d=json.loads(open(f'gpurun_out/{f}.json').read().strip().splitlines()[-1])
+        print(f,'value', d['value'], 'ms', d['ms_per_step'], '\n strong', d['strong_n100k']['value'], d['strong_n100k']['ms_per_step'], d['strong_n100k']['workload'][:40])
+    except Exception as e: print(f,'no json', e, open(f'gpurun_out/{f}.err').read()[-800:])
 PY
