@@ -358,3 +358,32 @@ def test_training_step_on_tensor_core_path_matches_oracle_grads():
     for k, v in tg.items():
         r = rel_to_max(_np(named[grad_name(k, True)].grad), v)
         assert r < (1e-3 if k in ("W1", "b1", "W2", "b2") else 5e-5), (k, r)
+
+
+def test_forward_bags_generic_route_fits_the_reported_workspace():
+    """with DSMIL_B200_GENERIC=1 forward_bags takes the per-bag generic loop; the workspace size reported by
+    dsmil_forward_bags_workspace_bytes must cover that route too (a small batch needs MORE there than the batched layout)."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from oracle import dsmil_oracle as orc\n"
+        "from helpers import build_net\n"
+        "p = orc.random_params(512, 2, 5, scale=2.0)\n"
+        "X = orc.synthetic_bag(1000, 512, 6, 'uniform')\n"
+        "net = build_net(p).eval()\n"
+        "with torch.no_grad():\n"
+        "    o = net.forward_bags([torch.from_numpy(X).cuda()])[0]\n"
+        "t = orc.forward(X, p)\n"
+        "assert np.array_equal(net.critical_instances(torch.from_numpy(X).cuda()).cpu().numpy(), t.idx)\n"
+        "B = o[3].cpu().numpy().reshape(2, 512)\n"
+        "assert float(np.max(np.abs(B - np.asarray(t.B).reshape(2, 512)))) < 1e-5 * float(np.max(np.abs(t.B)))\n"
+        "from dsmil_wsi_b200 import _lib, functional as Fn\n"
+        "from dsmil_wsi_b200.sharded import milnet_params\n"
+        "assert _lib.load().dsmil_forward_path(Fn.ParamPack(*milnet_params(net)).ref, 1000) == 1\n"
+        "print('GENERIC_OK')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DSMIL_B200_GENERIC="1"), capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "GENERIC_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
