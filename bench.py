@@ -23,6 +23,7 @@ extras  : torch_eager_gpu (the unmodified reference module through PyTorch eager
 `--impl reference` times the reference's CPU implementation alone.
 """
 import argparse
+import contextlib
 import ctypes
 import json
 import os
@@ -347,7 +348,123 @@ def run_extras(args, p, net, bags, dev, ms_per_step):
         ex["embed_resnet18_in"] = embed_leg(dev, refmod)
     except Exception as e:                                    # torchvision missing etc.: report, do not fail the bench
         ex["embed_resnet18_in"] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+    # (6) the patch loader + the whole compute_feats loop from JPEG FILES on disk (compute_feats.py:19-82)
+    try:
+        ex["embed_from_files"] = files_leg(dev, refmod)
+    except Exception as e:
+        ex["embed_from_files"] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
     return ex
+
+
+def synth_patch_files(n, seed=0, hw=224, quality=70):
+    """n JPEG files shaped like the reference's patches (deepzoom_tiler.py saves 224 x 224 tiles with PIL, quality 70,
+    PIL defaults = 4:2:0, standard Huffman tables): smooth stained-tissue-like blobs + noise, not white noise."""
+    import io
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:hw, 0:hw].astype(np.float32)
+    out = []
+    for _ in range(n):
+        img = np.zeros((hw, hw, 3), np.float32) + np.array([225.0, 190.0, 215.0], np.float32)
+        for _ in range(12):
+            cy, cx, r = rng.uniform(0, hw), rng.uniform(0, hw), rng.uniform(3, hw / 4)
+            img -= np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * r * r))[..., None] * rng.uniform(30, 140, 3).astype(np.float32)
+        img += rng.normal(0, 6, img.shape).astype(np.float32)
+        b = io.BytesIO()
+        Image.fromarray(np.clip(img, 0, 255).astype(np.uint8)).save(b, format="JPEG", quality=quality)
+        out.append(b.getvalue())
+    return out
+
+
+def files_leg(dev, refmod, n_files=1024, batch=128, workers=4):
+    """(a) the device JPEG loader alone on one 128-patch batch, against PIL on `workers` host threads (the reference's
+    DataLoader(num_workers=4)); (b) compute_feats over a bag folder of n_files patches, wall clock, CSV written:
+    this repo's loop (device decode / host decode) and the reference's own unmodified compute_feats.compute_feats."""
+    import shutil
+    import tempfile
+    import types
+    from concurrent.futures import ThreadPoolExecutor
+    import dsmil as mil
+    from dsmil_wsi_b200 import embed, jpeg
+    from oracle import stage_ref
+    distinct = synth_patch_files(batch, seed=5)
+    out = {"what": f"{n_files} patch files (224 x 224 JPEG, quality 70, PIL defaults; {batch} distinct images), batch {batch}, "
+                   f"{workers} loader workers, ResNet-18-InstanceNorm embedder, '%.4f' CSV written",
+           "bytes_per_file": int(np.mean([len(f) for f in distinct]))}
+    # (a) loader alone
+    pb = jpeg.parse_batch(distinct, pin=True)
+    dec = jpeg.JpegBatchDecoder(dev)
+    x = torch.empty(batch, 3, 224, 224, device=dev)
+    ms = cuda_time_ms(lambda: dec.decode(pb, out_f32=x), 10, warm=2)
+    st = dec.decode(pb, out_f32=x)
+    torch.cuda.synchronize()
+    if st.cpu().abs().sum().item() != 0:
+        raise RuntimeError("device JPEG decode reported a failure")
+    t0 = time.perf_counter()
+    for _ in range(3):
+        jpeg.parse_batch(distinct)
+    parse_ms = (time.perf_counter() - t0) / 3 * 1e3
+    with ThreadPoolExecutor(workers) as pool:
+        list(pool.map(embed._decode_u8, distinct[:16]))
+        t0 = time.perf_counter()
+        ref_imgs = list(pool.map(embed._decode_u8, distinct))
+        pil_ms = (time.perf_counter() - t0) * 1e3
+    same = bool(np.array_equal((x[0].permute(1, 2, 0) * 255).round().byte().cpu().numpy(), ref_imgs[0]))
+    out["loader_batch128"] = {"device_ms": ms, "device_patches_per_s": batch / (ms / 1e3), "host_parse_ms": parse_ms,
+                              "pil_threads_ms": pil_ms, "pil_patches_per_s": batch / (pil_ms / 1e3), "threads": workers,
+                              "speedup": pil_ms / ms, "first_patch_equals_pil": same,
+                              "h2d_bytes_device_route": int(pb.blob_bytes + pb.n * jpeg.header_bytes()),
+                              "h2d_bytes_reference": batch * 3 * 224 * 224 * 4,
+                              "what": "H2D of the files + k_jpeg_entropy/idct/color (CUDA events) vs PIL decode on host threads"}
+    # (b) the loop from a folder
+    root = tempfile.mkdtemp(prefix="dsmil_files_")
+    try:
+        bag = os.path.join(root, "in", "class0", "bag0")
+        os.makedirs(bag)
+        for i in range(n_files):
+            with open(os.path.join(bag, f"{i // 32}_{i % 32}.jpeg"), "wb") as f:
+                f.write(distinct[i % batch])
+        args = types.SimpleNamespace(batch_size=batch, num_workers=workers)
+        ours = make_embedder(mil, dev, True)
+
+        def run(fn, route=None):
+            if route is not None:
+                os.environ["DSMIL_B200_JPEG"] = route
+            best = None
+            for rep in range(2):                         # first pass warms cuDNN / the page cache
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                with contextlib.redirect_stdout(sys.stderr):          # both loops print progress; stdout carries the JSON line
+                    fn(os.path.join(root, f"out_{route}_{rep}"))
+                torch.cuda.synchronize()
+                best = time.perf_counter() - t0
+            os.environ.pop("DSMIL_B200_JPEG", None)
+            return best
+        t_dev = run(lambda sp: embed.compute_feats(args, [bag], ours, sp), "gpu")
+        t_host = run(lambda sp: embed.compute_feats(args, [bag], ours, sp), "host")
+        out["compute_feats"] = {"value": n_files / t_dev, "unit": "patches/s", "seconds": t_dev,
+                                "host_decode_route_patches_per_s": n_files / t_host, "host_decode_route_seconds": t_host}
+        rcf = stage_ref.load_reference_compute_feats()
+        if rcf is not None and refmod is not None:
+            ref = make_embedder(refmod, dev, False)
+            t_ref = run(lambda sp: rcf.compute_feats(args, [bag], ref, sp, "single"))
+            out["compute_feats"].update({"reference_patches_per_s": n_files / t_ref, "reference_seconds": t_ref,
+                                         "speedup": t_ref / t_dev,
+                                         "reference": "oracle/_ref/compute_feats.py compute_feats (unmodified): DataLoader workers + PIL "
+                                                      "+ .float().cuda() + eager backbone + pandas CSV, same GPU"})
+            a = open(os.path.join(root, "out_gpu_1", "class0", "bag0.csv")).read()
+            b = open(os.path.join(root, "out_None_1", "class0", "bag0.csv")).read()
+            fa = np.loadtxt(io_lines(a), delimiter=",", skiprows=1)
+            fb = np.loadtxt(io_lines(b), delimiter=",", skiprows=1)
+            out["compute_feats"]["max_abs_csv_diff_vs_reference"] = float(np.abs(fa - fb).max())
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    return out
+
+
+def io_lines(text):
+    import io
+    return io.StringIO(text)
 
 
 def make_embedder(modlib, dev, fuse):

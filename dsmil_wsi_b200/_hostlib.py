@@ -15,6 +15,9 @@ SIGNATURES = {
     "dsmil_csv_write_bag": (C.c_int64, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]),
     "dsmil_csv_shape": (C.c_int32, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "dsmil_csv_parse_bag": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_int64)]),
+    "dsmil_jpeg_header_bytes": (C.c_int32, []),
+    "dsmil_jpeg_parse": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "dsmil_jpeg_parse_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 ERRORS = {-1: "bad argument", -2: "I/O error", -3: "ragged row (field count differs from the header)",
           -4: "field is not a number", -5: "output buffer too small"}

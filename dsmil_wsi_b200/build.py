@@ -15,7 +15,7 @@ LIB = os.path.join(LIBDIR, "libdsmil_b200.so")
 SOURCES = ["abi.cu"]
 HOST_CSRC = os.path.join(HERE, "csrc_host")
 HOST_LIB = os.path.join(LIBDIR, "libdsmil_host.so")
-HOST_SOURCES = ["bagcsv.c"]
+HOST_SOURCES = ["bagcsv.c", "jpegparse.c"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -62,6 +62,7 @@ def _host_digest():
     for f in sorted(os.listdir(HOST_CSRC)):
         h.update(f.encode())
         h.update(open(os.path.join(HOST_CSRC, f), "rb").read())
+    h.update(open(os.path.join(CSRC, "jpeg_core.h"), "rb").read())      # shared with the device kernels
     return h.hexdigest()
 
 

@@ -17,6 +17,7 @@
 #include "fwd_batched.cuh"
 #include "fwd_pair.cuh"
 #include "embed_kernels.cuh"
+#include "jpeg_kernels.cuh"
 
 namespace dsmil {
 
@@ -571,6 +572,51 @@ int dsmil_instnorm_act(const float* x, const float* residual, float* y, int64_t 
   DSMIL_REQUIRE(planes < (1ll << 31), "too many planes");
   if (planes == 0) return 0;
   return launch_instnorm(x, residual, y, planes, HW, eps, relu, static_cast<cudaStream_t>(stream));
+}
+
+static JpegBatch carve_jpeg(void* ws, size_t cap, int n, int H, int W, int64_t blob_bytes, size_t* need) {
+  Carver cv(ws, cap);
+  JpegBatch a{};
+  a.n = n; a.H = H; a.W = W;
+  a.plane_elems = jpeg_plane_elems(H, W);
+  a.unstuffed = cv.take<uint8_t>(static_cast<size_t>(blob_bytes) + 64);
+  a.coef = cv.take<int16_t>(static_cast<size_t>(3) * a.plane_elems * n);
+  a.planes = cv.take<uint8_t>(static_cast<size_t>(3) * a.plane_elems * n);
+  *need = cv.off;
+  return a;
+}
+
+int32_t dsmil_jpeg_header_bytes_dev(void) { return static_cast<int32_t>(sizeof(dsmil_jpeg_header)); }
+
+int64_t dsmil_jpeg_workspace_bytes(int32_t n, int32_t H, int32_t W, int64_t blob_bytes) {
+  if (n < 0 || H < 1 || W < 1 || H > 65535 || W > 65535 || blob_bytes < 0) return -1;
+  size_t need = 0;
+  carve_jpeg(nullptr, 0, n, H, W, blob_bytes, &need);
+  return static_cast<int64_t>(need);
+}
+
+int dsmil_jpeg_decode_batch(const uint8_t* blob, int64_t blob_bytes, const void* headers, int32_t n, int32_t H, int32_t W,
+                            uint8_t* out_u8, float* out_f32, int32_t* status, void* workspace, int64_t workspace_bytes,
+                            void* stream) {
+  DSMIL_REQUIRE(n >= 0 && H >= 1 && W >= 1 && H <= 65535 && W <= 65535 && blob_bytes >= 0, "bad arguments");
+  if (n == 0) return 0;
+  DSMIL_REQUIRE(blob && headers && status && workspace && (out_u8 || out_f32), "null pointer");
+  DSMIL_REQUIRE((reinterpret_cast<uintptr_t>(headers) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
+                (out_f32 == nullptr || (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0) &&
+                (out_u8 == nullptr || (reinterpret_cast<uintptr_t>(out_u8) & 3) == 0),
+                "headers must be 16-byte, workspace 256-byte, out_f32 16-byte, out_u8 4-byte aligned");
+  size_t need = 0;
+  JpegBatch a = carve_jpeg(workspace, static_cast<size_t>(workspace_bytes), n, H, W, blob_bytes, &need);
+  if (static_cast<int64_t>(need) > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %lld", need, static_cast<long long>(workspace_bytes));
+    return DSMIL_ERR_WORKSPACE;
+  }
+  a.blob = blob;
+  a.hdr = static_cast<const dsmil_jpeg_header*>(headers);
+  a.out_u8 = out_u8;
+  a.out_f32 = out_f32;
+  a.status = status;
+  return launch_jpeg_decode(a, static_cast<cudaStream_t>(stream));
 }
 
 int dsmil_profile_enable(int on) {

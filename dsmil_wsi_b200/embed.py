@@ -5,9 +5,13 @@ Reference loop per bag: DataLoader(batch 128, 4 workers: PIL open + VF.to_tensor
 -> Python list -> DataFrame.to_csv('%.4f').
 
 Here:
-  * decode stays on the host (PIL, thread pool) but patches cross PCIe as **uint8 HWC** from pinned, reused
-    staging buffers (19 MB per 128-patch batch instead of 77 MB), two batches in flight on a copy stream;
-  * uint8 -> fp32 CHW / 255 is `dsmil_patches_u8_to_f32` on the device (bit-identical to VF.to_tensor);
+  * the patch FILES cross PCIe (~2 MB per 128-patch batch instead of 77 MB of fp32) and are decoded on the device
+    (jpeg.py / csrc/jpeg_kernels.cuh: Huffman decoding one warp per patch, IDCT, upsampling, colour, /255 -- bit for
+    bit PIL's output), on a side stream under the backbone of the previous batch; the worker threads only read files;
+  * a batch holding a file the device path does not take (progressive, CMYK, ...) goes through PIL -- the reference's
+    own decoder -- and crosses PCIe as **uint8 HWC** from pinned staging buffers (19 MB per batch);
+    uint8 -> fp32 CHW / 255 is then `dsmil_patches_u8_to_f32` (bit-identical to VF.to_tensor).
+    `DSMIL_B200_JPEG=host` forces that route for every batch, `=gpu` forbids it (raises instead);
   * the backbone is the caller's module (torchvision ResNet via cuDNN -- library code, as in the reference);
     the instance classifier head is `dsmil_instance_scores` (our kernel) through IClassifier;
   * features stay on the device for the whole bag: ONE D2H per bag, or none when `sink` hands the bag
@@ -53,11 +57,18 @@ def list_tree_patches(bag_dir: str):
     return low, high
 
 
-def _decode_u8(path: str) -> np.ndarray:
+def _decode_u8(src) -> np.ndarray:
+    """PIL decode of a path or of the bytes of a file (the host route of a batch)."""
+    import io
     from PIL import Image
-    with Image.open(path) as im:
+    with Image.open(io.BytesIO(src) if isinstance(src, (bytes, bytearray, memoryview)) else src) as im:
         a = np.asarray(im.convert("RGB") if im.mode != "RGB" else im, dtype=np.uint8)
     return np.array(a, copy=True) if not a.flags.writeable else a  # HWC uint8 (writable: torch.from_numpy)
+
+
+def _read_file(path: str) -> bytes:
+    with open(path, "rb") as f:
+        return f.read()
 
 
 def patches_to_float(u8_hwc: torch.Tensor) -> torch.Tensor:
@@ -117,20 +128,61 @@ def write_bag_csv(feats: np.ndarray, save_path: str, bag_dir: str) -> str:
 
 
 class _Staging:
-    """Two pinned uint8 batch buffers + their device twins; batch b+1 is decoded/copied while b is embedded."""
+    """Two slots, each: pinned file blob + headers (device route) or a pinned uint8 batch (host route) and their
+    device twins; batch b+1 is read / parsed / copied / decoded while batch b is embedded."""
 
     def __init__(self, batch: int, H: int, W: int, device):
-        self.host = [torch.empty(batch, H, W, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
-        self.dev = [torch.empty(batch, H, W, 3, dtype=torch.uint8, device=device) for _ in range(2)]
+        from . import jpeg
+        self.batch, self.H, self.W, self.device = batch, H, W, device
+        self.host_u8 = [None, None]                      # allocated on first use of the host route
+        self.dev_u8 = [None, None]
+        self.dev_f32 = [None, None]                      # allocated on first use of the device route
+        self.blob = [jpeg._Pinned(), jpeg._Pinned()]
+        self.hdr = [jpeg._Pinned(), jpeg._Pinned()]
+        self.status_host = [torch.zeros(batch, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.status_names = [None, None]
         self.copied = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
         self.stream = torch.cuda.Stream(device=device)
+        self.decoder = jpeg.JpegBatchDecoder(device)
+
+    def u8(self, s):
+        if self.host_u8[s] is None:
+            self.host_u8[s] = torch.empty(self.batch, self.H, self.W, 3, dtype=torch.uint8).pin_memory()
+            self.dev_u8[s] = torch.empty(self.batch, self.H, self.W, 3, dtype=torch.uint8, device=self.device)
+        return self.host_u8[s], self.dev_u8[s]
+
+    def f32(self, s):
+        if self.dev_f32[s] is None:
+            self.dev_f32[s] = torch.empty(self.batch, 3, self.H, self.W, dtype=torch.float32, device=self.device)
+        return self.dev_f32[s]
+
+    def check_status(self, s):
+        """Raises if the last device decode of slot s reported a file it could not decode (call after its
+        `copied` event has completed)."""
+        names = self.status_names[s]
+        if names is None:
+            return
+        self.status_names[s] = None
+        st = self.status_host[s][:len(names)].numpy()
+        if np.any(st != 0):
+            from . import jpeg
+            i = int(np.flatnonzero(st)[0])
+            raise RuntimeError(f"JPEG decode of {names[i]} failed on the device: {jpeg.STATUS.get(int(st[i]), int(st[i]))}")
+
+
+def jpeg_route() -> str:
+    r = os.environ.get("DSMIL_B200_JPEG", "auto")
+    if r not in ("auto", "gpu", "host"):
+        raise ValueError(f"DSMIL_B200_JPEG={r!r}: expected auto, gpu or host")
+    return r
 
 
 @torch.no_grad()
 def embed_bag(paths: Sequence[str], i_classifier, batch_size: int = 128, num_workers: int = 4,
               device: Optional[torch.device] = None):
     """Features [N, D] (device) and instance scores [N, C] (device) of one bag of patch files."""
+    from . import jpeg
     dev = device or next(i_classifier.parameters()).device
     if dev.type != "cuda":
         raise RuntimeError("embed_bag needs the model on a CUDA device (no CPU path)")
@@ -141,6 +193,7 @@ def embed_bag(paths: Sequence[str], i_classifier, batch_size: int = 128, num_wor
     if fe is not None and os.environ.get("DSMIL_B200_FUSE_IN", "1") != "0":
         from .embedder import fuse_instance_norm            # InstanceNorm + residual + ReLU of the backbone: one kernel each
         fuse_instance_norm(fe)                               # (idempotent; leaves parameters / state_dict untouched)
+    route = jpeg_route()
     first = _decode_u8(paths[0])
     H, W = first.shape[:2]
     feats_out, cls_out = [], []
@@ -149,35 +202,65 @@ def embed_bag(paths: Sequence[str], i_classifier, batch_size: int = 128, num_wor
         compute = torch.cuda.current_stream()
         for s in range(2):
             st.consumed[s].record(compute)
+            st.copied[s].record(st.stream)
         batches = [paths[i:i + batch_size] for i in range(0, len(paths), batch_size)]
-        pending = None
 
         def stage(bi):
             s = bi % 2
-            imgs = list(pool.map(_decode_u8, batches[bi]))
-            st.consumed[s].synchronize()                    # the previous user of this slot has read it
-            hb = st.host[s]
+            names = batches[bi]
+            n = len(names)
+            on_device = False
+            files = None
+            if route != "host":
+                files = list(pool.map(_read_file, names))
+                st.copied[s].synchronize()                  # the pinned blob / headers of this slot are free again
+                st.check_status(s)
+                pb = jpeg.parse_batch(files, st.blob[s], st.hdr[s], pin=True)
+                on_device = pb.bad == 0 and (pb.H, pb.W) == (H, W)
+                if not on_device and route == "gpu":
+                    raise RuntimeError(f"DSMIL_B200_JPEG=gpu, but {pb.bad} file(s) of the batch starting at {names[0]} "
+                                       f"are not decodable on the device (statuses {pb.statuses.tolist()})")
+            st.consumed[s].synchronize()                    # the previous user of this slot's device buffers has read them
+            if on_device:
+                out = st.f32(s)
+                st.stream.wait_event(st.consumed[s])
+                status = st.decoder.decode(pb, out_f32=out[:n], stream=st.stream)
+                with torch.cuda.stream(st.stream):
+                    st.status_host[s][:n].copy_(status, non_blocking=True)
+                    st.copied[s].record(st.stream)
+                st.status_names[s] = names
+                return s, n, True
+            imgs = list(pool.map(_decode_u8, files if files is not None else names))
+            hb, db = st.u8(s)
+            st.copied[s].synchronize()
             for j, im in enumerate(imgs):
                 if im.shape != (H, W, 3):
-                    raise ValueError(f"patch {batches[bi][j]} is {im.shape}, expected {(H, W, 3)}")
+                    raise ValueError(f"patch {names[j]} is {im.shape}, expected {(H, W, 3)}")
                 hb[j].copy_(torch.from_numpy(im))
-            n = len(imgs)
             with torch.cuda.stream(st.stream):
-                st.dev[s][:n].copy_(hb[:n], non_blocking=True)
+                db[:n].copy_(hb[:n], non_blocking=True)
                 st.copied[s].record(st.stream)
-            return s, n
+            return s, n, False
 
         pending = stage(0)
         for bi in range(len(batches)):
-            s, n = pending
+            s, n, on_device = pending
             compute.wait_event(st.copied[s])
-            x = patches_to_float(st.dev[s][:n])
-            st.consumed[s].record(compute)
+            if on_device:
+                x = st.f32(s)[:n]
+            else:
+                x = patches_to_float(st.dev_u8[s][:n])
+                st.consumed[s].record(compute)
             if bi + 1 < len(batches):
                 pending = stage(bi + 1)                     # overlaps with the backbone of this batch
             feats, classes = i_classifier(x)
+            if on_device:
+                st.consumed[s].record(compute)              # the backbone has read the decoded batch in place
             feats_out.append(feats)
             cls_out.append(classes)
+        for s in range(2):
+            st.copied[s].synchronize()
+            st.check_status(s)
     return torch.cat(feats_out), torch.cat(cls_out)
 
 

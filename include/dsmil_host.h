@@ -27,6 +27,18 @@ int32_t dsmil_csv_shape(const char* buf, int64_t len, int64_t* N, int32_t* D);
  * field); empty field = NaN.  On error *bad_line holds the 1-based data-line number.  Returns 0. */
 int32_t dsmil_csv_parse_bag(const char* buf, int64_t len, float* out, int64_t N, int32_t D, int64_t* bad_line);
 
+/* Host half of the device JPEG loader (reference: compute_feats.py:26-29 `Image.open`; device half:
+ * dsmil_jpeg_decode_batch in include/dsmil_b200.h).  Parses the marker segments of JPEG files into fixed-size
+ * header records (dsmil_jpeg_header_bytes() each; layout in dsmil_wsi_b200/csrc/jpeg_core.h: geometry, sampling,
+ * quantisation and Huffman tables, where the entropy-coded segment lies).  No pixel work on the host.
+ * Status of a file: 0 decodable on the device, -1 corrupt, -2 valid JPEG outside the device path (progressive,
+ * arithmetic, 12-bit, CMYK / Adobe colour, other samplings, multi-scan).
+ * dsmil_jpeg_parse_batch: n files back to back in `blob`, file i = [offsets[i], offsets[i+1]) (offsets has n+1
+ * entries); fills headers[0..n) and returns how many files are NOT decodable on the device (< 0: bad argument). */
+int32_t dsmil_jpeg_header_bytes(void);
+int32_t dsmil_jpeg_parse(const uint8_t* file, int64_t len, void* header);
+int32_t dsmil_jpeg_parse_batch(const uint8_t* blob, const int64_t* offsets, int32_t n, void* headers);
+
 #ifdef __cplusplus
 }
 #endif

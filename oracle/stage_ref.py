@@ -4,6 +4,8 @@ NOT gpurun-ignored) so that they travel to the GPU box, where ``/root/reference`
 TEST / BENCH INFRASTRUCTURE ONLY.  Nothing under ``dsmil_wsi_b200/`` reads ``oracle/_ref``.  Users:
   * ``bench.py --impl reference`` and the ``torch_eager_gpu`` leg: the reference's own ``MILNet`` timed on the
     host cores / through PyTorch eager on the GPU (``cpu_baseline.kind == "reference"``);
+  * ``bench.py``'s ``embed_from_files`` leg: the reference's own ``compute_feats.compute_feats`` loop (DataLoader
+    workers + PIL + ``.float().cuda()`` + pandas CSV) run on a folder of patch files;
   * ``tests/test_zz_acceptance_gpu.py``: the unmodified ``train_tcga.py`` / ``train_mil.py`` run with THIS repo's
     ``dsmil.py`` shim ahead of them on ``sys.path`` (the callers are the acceptance harness).
 
@@ -21,7 +23,7 @@ import shutil
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = os.environ.get("DSMIL_REFERENCE_DIR", "/root/reference")
 REF_DST = os.path.join(HERE, "_ref")
-FILES = ("dsmil.py", "train_tcga.py", "train_mil.py")
+FILES = ("dsmil.py", "train_tcga.py", "train_mil.py", "compute_feats.py")
 
 
 def staged(name: str = "dsmil.py"):
@@ -62,6 +64,34 @@ def load_reference_dsmil():
     spec = importlib.util.spec_from_file_location("_ref_dsmil", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
+    return mod
+
+
+
+
+def load_reference_compute_feats():
+    """Imports the staged, unmodified reference ``compute_feats.py`` as ``_ref_compute_feats`` with ITS ``dsmil``
+    (the staged reference module) bound to the name it imports.  Returns the module or None."""
+    import importlib.util
+    import sys
+    path = staged("compute_feats.py")
+    ref_dsmil = load_reference_dsmil()
+    if path is None or ref_dsmil is None:
+        return None
+    if "_ref_compute_feats" in sys.modules:
+        return sys.modules["_ref_compute_feats"]
+    saved = sys.modules.get("dsmil")
+    sys.modules["dsmil"] = ref_dsmil
+    try:
+        spec = importlib.util.spec_from_file_location("_ref_compute_feats", path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["_ref_compute_feats"] = mod
+        spec.loader.exec_module(mod)
+    finally:
+        if saved is not None:
+            sys.modules["dsmil"] = saved
+        else:
+            sys.modules.pop("dsmil", None)
     return mod
 
 

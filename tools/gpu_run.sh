@@ -1,6 +1,17 @@
+#!/bin/bash
+# scratch script for one gpurun call
 mkdir -p gpurun_out
-for t in 1 2 3; do
-  DSMIL_B200_TILES_PER_REC=$t timeout 300 python bench.py --no-extras --cpu-seconds 1 > gpurun_out/r2_bench_tpr$t.json 2> gpurun_out/r2_bench_tpr$t.err
-  python -c "
-import json; d=json.loads(open('gpurun_out/r2_bench_tpr$t.json').read().strip().splitlines()[-1]); print('tiles/rec=$t', 'ms', d['ms_per_step'], d['roofline']['per_kernel_ms'])"
-done
+cd /root/repo
+timeout 600 python -m pytest tests/test_zz_jpeg_gpu.py -x -q 2>&1 | tail -15 > gpurun_out/r2_jpeg_pytest.txt
+cat gpurun_out/r2_jpeg_pytest.txt
+timeout 600 python - > gpurun_out/r2_files_leg.json 2> gpurun_out/r2_files_leg.err <<'PY'
+import json, sys, torch
+sys.path.insert(0, '/root/repo')
+import bench
+dev = torch.device('cuda', 0)
+torch.cuda.set_device(0)
+refmod = bench.load_reference_module()
+print(json.dumps(bench.files_leg(dev, refmod), indent=1))
+PY
+tail -5 gpurun_out/r2_files_leg.err
+cat gpurun_out/r2_files_leg.json
