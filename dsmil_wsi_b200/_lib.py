@@ -37,10 +37,12 @@ SIGNATURES = {
     "dsmil_gather_rows": (C.c_int, [C.c_void_p, c_i64, C.c_int32, C.c_void_p, c_i64, C.c_void_p, C.c_void_p]),
     "dsmil_patches_u8_to_f32": (C.c_int, [C.c_void_p, c_i64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "dsmil_instnorm_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_i64, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
+    "dsmil_instnorm_act_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_i64, C.c_int32, C.c_int32, C.c_float, C.c_int32,
+                                          C.c_void_p]),
     "dsmil_jpeg_header_bytes_dev": (C.c_int32, []),
     "dsmil_jpeg_workspace_bytes": (c_i64, [C.c_int32, C.c_int32, C.c_int32, c_i64]),
     "dsmil_jpeg_decode_batch": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
-                                          C.c_void_p, C.c_void_p, C.c_void_p, c_i64, C.c_void_p]),
+                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, c_i64, C.c_void_p]),
     "dsmil_profile_enable": (C.c_int, [C.c_int]),
     "dsmil_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "dsmil_debug_set_trace": (C.c_int, [C.c_void_p]),

@@ -574,6 +574,15 @@ int dsmil_instnorm_act(const float* x, const float* residual, float* y, int64_t 
   return launch_instnorm(x, residual, y, planes, HW, eps, relu, static_cast<cudaStream_t>(stream));
 }
 
+int dsmil_instnorm_act_nhwc(const float* x, const float* residual, float* y, int64_t N, int32_t HW, int32_t C, float eps,
+                            int32_t relu, void* stream) {
+  DSMIL_REQUIRE(N >= 0 && HW >= 1 && C >= 32 && C % 32 == 0 && eps >= 0.f && (N == 0 || (x && y)),
+                "bad arguments (C must be a multiple of 32)");
+  DSMIL_REQUIRE(N * (C / 32) < (1ll << 31), "too many (sample, channel group) slabs");
+  if (N == 0) return 0;
+  return launch_instnorm_nhwc(x, residual, y, N, HW, C, eps, relu, static_cast<cudaStream_t>(stream));
+}
+
 static JpegBatch carve_jpeg(void* ws, size_t cap, int n, int H, int W, int64_t blob_bytes, size_t* need) {
   Carver cv(ws, cap);
   JpegBatch a{};
@@ -596,9 +605,10 @@ int64_t dsmil_jpeg_workspace_bytes(int32_t n, int32_t H, int32_t W, int64_t blob
 }
 
 int dsmil_jpeg_decode_batch(const uint8_t* blob, int64_t blob_bytes, const void* headers, int32_t n, int32_t H, int32_t W,
-                            uint8_t* out_u8, float* out_f32, int32_t* status, void* workspace, int64_t workspace_bytes,
-                            void* stream) {
-  DSMIL_REQUIRE(n >= 0 && H >= 1 && W >= 1 && H <= 65535 && W <= 65535 && blob_bytes >= 0, "bad arguments");
+                            uint8_t* out_u8, float* out_f32, int32_t f32_channels_last, int32_t* status, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
+  DSMIL_REQUIRE(n >= 0 && H >= 1 && W >= 1 && H <= 65535 && W <= 65535 && blob_bytes >= 0 &&
+                (f32_channels_last == 0 || f32_channels_last == 1), "bad arguments");
   if (n == 0) return 0;
   DSMIL_REQUIRE(blob && headers && status && workspace && (out_u8 || out_f32), "null pointer");
   DSMIL_REQUIRE((reinterpret_cast<uintptr_t>(headers) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
@@ -615,6 +625,7 @@ int dsmil_jpeg_decode_batch(const uint8_t* blob, int64_t blob_bytes, const void*
   a.hdr = static_cast<const dsmil_jpeg_header*>(headers);
   a.out_u8 = out_u8;
   a.out_f32 = out_f32;
+  a.f32_hwc = f32_channels_last;
   a.status = status;
   return launch_jpeg_decode(a, static_cast<cudaStream_t>(stream));
 }

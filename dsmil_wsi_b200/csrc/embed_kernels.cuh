@@ -10,7 +10,16 @@
 //   k_instnorm_warp    one WARP per plane of <= 1024 elements (56x56 is handled by the CTA kernel; 28x28, 14x14, 7x7
 //                      here): the plane lives in registers, 8 planes per CTA
 //
-// HBM-bound: algorithmic bytes = 8 B per element (+ 4 with a residual).  NCHW fp32 contiguous; in place allowed.
+//   k_instnorm_nhwc    the channels-last form (cuDNN's NHWC convolution kernels run the ResNet-18 convolutions 1.5x
+//                      faster than its NCHW ones on B200: 2.43 vs 3.70 ms per 128-patch batch, profiles/
+//                      r2_exp_channels_last.json).  Memory is [n][HW][C]; one CTA per (sample, 32-channel group),
+//                      lane = channel, warps stride over the pixels, so every warp load is one 128-byte row segment.
+//                      Statistics in ONE pass as shifted sums (x - x0, x0 = the channel's first pixel: no
+//                      catastrophic cancellation for activations whose mean is far from 0), second pass normalises;
+//                      the slab a CTA reads twice is <= 1.6 MB and was just written by the convolution, i.e. the
+//                      second read is an L2 hit for every layer but the 112x112 stem.
+//
+// HBM-bound: algorithmic bytes = 8 B per element (+ 4 with a residual).  fp32 contiguous; in place allowed.
 #pragma once
 #include "common.cuh"
 
@@ -113,6 +122,55 @@ k_instnorm_warp(const float* __restrict__ x, const float* __restrict__ res, floa
       y[base + i] = o;
     }
   }
+}
+
+constexpr int kNhwcWarps = 16;
+
+__global__ void __launch_bounds__(32 * kNhwcWarps)
+k_instnorm_nhwc(const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ y, int HW, int C, float eps,
+                int relu) {
+  __shared__ float s_a[kNhwcWarps][32], s_b[kNhwcWarps][32];
+  const int groups = C >> 5;
+  const int n = blockIdx.x / groups, g = blockIdx.x - n * groups;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t base = (static_cast<size_t>(n) * HW) * C + (g << 5) + lane;
+  const float* xp = x + base;
+  const float x0 = __ldg(xp);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+  for (int p = warp; p < HW; p += kNhwcWarps) {
+    const float d = __ldg(xp + static_cast<size_t>(p) * C) - x0;
+    s1 += d;
+    s2 = fmaf(d, d, s2);
+  }
+  s_a[warp][lane] = s1;
+  s_b[warp][lane] = s2;
+  __syncthreads();
+  s1 = 0.f; s2 = 0.f;
+#pragma unroll
+  for (int w = 0; w < kNhwcWarps; ++w) { s1 += s_a[w][lane]; s2 += s_b[w][lane]; }   // fixed order
+  const float inv = 1.f / static_cast<float>(HW);
+  const float dm = s1 * inv;                                    // mean - x0
+  const float mean = x0 + dm;
+  const float var = fmaxf(fmaf(-dm, s1, s2) * inv, 0.f);        // (S2 - S1^2 / HW) / HW, biased as F.instance_norm
+  const float rstd = rsqrtf(var + eps);
+  float* yp = y + base;
+  const float* rp = res ? res + base : nullptr;
+#pragma unroll 4
+  for (int p = warp; p < HW; p += kNhwcWarps) {
+    const size_t o = static_cast<size_t>(p) * C;
+    float v = (xp[o] - mean) * rstd;
+    if (rp) v += __ldg(rp + o);
+    if (relu) v = fmaxf(v, 0.f);
+    yp[o] = v;
+  }
+}
+
+inline int launch_instnorm_nhwc(const float* x, const float* res, float* y, long long N, int HW, int C, float eps, int relu,
+                                cudaStream_t st) {
+  k_instnorm_nhwc<<<static_cast<unsigned>(N * (C >> 5)), 32 * kNhwcWarps, 0, st>>>(x, res, y, HW, C, eps, relu);
+  DSMIL_LAUNCH_OK("k_instnorm_nhwc");
+  return 0;
 }
 
 inline int launch_instnorm(const float* x, const float* res, float* y, long long planes, int HW, float eps, int relu,

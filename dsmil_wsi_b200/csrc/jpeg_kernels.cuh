@@ -39,7 +39,8 @@ struct JpegBatch {
   int16_t* coef;                  // [n][3][plane_elems], zeroed before k_jpeg_entropy
   uint8_t* planes;                // [n][3][plane_elems]
   uint8_t* out_u8;                // [n][H][W][3] or null
-  float* out_f32;                 // [n][3][H][W] or null
+  float* out_f32;                 // [n][3][H][W] (f32_hwc == 0) or [n][H][W][3] (f32_hwc == 1: torch.channels_last) or null
+  int f32_hwc;
   int32_t* status;                // [n]
 };
 
@@ -210,7 +211,22 @@ k_jpeg_color(JpegBatch a) {
       for (int i = 0; i < nx; ++i) { o[3 * i] = rgb[i][0]; o[3 * i + 1] = rgb[i][1]; o[3 * i + 2] = rgb[i][2]; }
     }
   }
-  if (a.out_f32) {
+  if (a.out_f32 && a.f32_hwc) {
+    float* o = a.out_f32 + (static_cast<long long>(img) * a.H * a.W + static_cast<long long>(y) * a.W + x0) * 3;
+    float f[12];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) f[3 * i + ch] = __fdiv_rn(static_cast<float>(rgb[i][ch]), 255.f);
+    if (nx == 4 && (a.W & 3) == 0) {                    // 48 bytes, 16-byte aligned when W % 4 == 0
+      float4* o4 = reinterpret_cast<float4*>(o);
+      o4[0] = make_float4(f[0], f[1], f[2], f[3]);
+      o4[1] = make_float4(f[4], f[5], f[6], f[7]);
+      o4[2] = make_float4(f[8], f[9], f[10], f[11]);
+    } else {
+      for (int i = 0; i < 3 * nx; ++i) o[i] = f[i];
+    }
+  } else if (a.out_f32) {
     const long long hw = static_cast<long long>(a.H) * a.W;
     float* o = a.out_f32 + static_cast<long long>(img) * 3 * hw + static_cast<long long>(y) * a.W + x0;
 #pragma unroll

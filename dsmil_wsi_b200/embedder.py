@@ -2,7 +2,8 @@
 ResNet built with `norm_layer=nn.InstanceNorm2d` (compute_feats.py:146-170).  The convolutions stay cuDNN library
 GEMMs; everything between them -- instance norm, the residual add and the ReLU, which the framework runs as two or three
 memory-bound passes per convolution -- goes through ONE kernel of libdsmil_b200.so (`dsmil_instnorm_act`,
-csrc/embed_kernels.cuh).
+csrc/embed_kernels.cuh), in NCHW or in channels-last memory (`dsmil_instnorm_act_nhwc`): cuDNN runs this backbone's
+convolutions 1.5x faster in channels-last on B200, so `embed.embed_bag` switches the backbone and its input to it.
 
     fuse_instance_norm(resnet)   rewires the blocks of a torchvision ResNet in place (parameters, buffers and
                                  state_dict keys untouched, so the reference's embedder checkpoints still load);
@@ -21,25 +22,41 @@ from . import _lib
 from . import functional as Fn
 
 
+def _is_channels_last(t: torch.Tensor) -> bool:
+    """True NHWC memory (a tensor with C == 1 or H*W == 1 satisfies both layouts and counts as NCHW)."""
+    return (not t.is_contiguous()) and t.is_contiguous(memory_format=torch.channels_last)
+
+
 def instnorm_act(x: torch.Tensor, residual: torch.Tensor | None = None, relu: bool = True, eps: float = 1e-5,
                  out: torch.Tensor | None = None) -> torch.Tensor:
-    """y = [relu](instance_norm(x) [+ residual]) for an NCHW fp32 tensor, one pass.  `out` may be `x` (in place)."""
+    """y = [relu](instance_norm(x) [+ residual]) for a 4-D fp32 tensor, one kernel.  NCHW-contiguous and
+    torch.channels_last inputs each have their own kernel (no layout conversion); the result keeps x's layout.
+    `out` may be `x` (in place)."""
     Fn.require_cuda(x, "the activation tensor")
     if x.dtype != torch.float32 or x.dim() != 4:
-        raise TypeError(f"instnorm_act wants a 4-D fp32 NCHW tensor, got {tuple(x.shape)} {x.dtype}")
-    x = x.contiguous()
+        raise TypeError(f"instnorm_act wants a 4-D fp32 tensor, got {tuple(x.shape)} {x.dtype}")
     N, Cc, H, W = x.shape
+    nhwc = _is_channels_last(x) and Cc % 32 == 0
+    fmt = torch.channels_last if nhwc else torch.contiguous_format
+    if not nhwc:
+        x = x.contiguous()
     if residual is not None:
         if residual.shape != x.shape or residual.dtype != torch.float32:
             raise ValueError("residual must match x")
-        residual = residual.contiguous()
-    y = torch.empty_like(x) if out is None else out
-    if y.shape != x.shape or not y.is_contiguous():
-        raise ValueError("out must be a contiguous tensor of x's shape")
+        residual = residual.contiguous(memory_format=fmt)
+    y = torch.empty_like(x, memory_format=fmt) if out is None else out
+    if y.shape != x.shape or not y.is_contiguous(memory_format=fmt):
+        raise ValueError("out must be a tensor of x's shape and memory layout")
     with torch.cuda.device(x.device):
-        rc = _lib.load().dsmil_instnorm_act(x.data_ptr(), Fn._ptr(residual), y.data_ptr(), N * Cc, H * W, float(eps),
-                                            int(bool(relu)), Fn._stream())
-        _lib.check(rc, "dsmil_instnorm_act")
+        lib = _lib.load()
+        if nhwc:
+            rc = lib.dsmil_instnorm_act_nhwc(x.data_ptr(), Fn._ptr(residual), y.data_ptr(), N, H * W, Cc, float(eps),
+                                             int(bool(relu)), Fn._stream())
+            _lib.check(rc, "dsmil_instnorm_act_nhwc")
+        else:
+            rc = lib.dsmil_instnorm_act(x.data_ptr(), Fn._ptr(residual), y.data_ptr(), N * Cc, H * W, float(eps),
+                                        int(bool(relu)), Fn._stream())
+            _lib.check(rc, "dsmil_instnorm_act")
     return y
 
 

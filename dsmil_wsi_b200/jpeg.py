@@ -103,9 +103,19 @@ class JpegBatchDecoder:
             raise ValueError("the first file of the batch is not decodable on the device; route the batch elsewhere")
         hb = header_bytes()
         n, H, W = pb.n, pb.H, pb.W
-        for t, shape, dt in ((out_f32, (n, 3, H, W), torch.float32), (out_u8, (n, H, W, 3), torch.uint8)):
-            if t is not None and (tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != self.device):
-                raise ValueError(f"output must be a contiguous {dt} tensor of shape {shape} on {self.device}")
+        channels_last = 0
+        if out_f32 is not None:
+            if tuple(out_f32.shape) != (n, 3, H, W) or out_f32.dtype != torch.float32 or out_f32.device != self.device:
+                raise ValueError(f"out_f32 must be a float32 tensor of shape {(n, 3, H, W)} on {self.device}")
+            if out_f32.is_contiguous():
+                channels_last = 0
+            elif out_f32.is_contiguous(memory_format=torch.channels_last):
+                channels_last = 1                          # same values, [n, H, W, 3] in memory
+            else:
+                raise ValueError("out_f32 must be contiguous (NCHW) or torch.channels_last")
+        if out_u8 is not None and (tuple(out_u8.shape) != (n, H, W, 3) or out_u8.dtype != torch.uint8 or
+                                   not out_u8.is_contiguous() or out_u8.device != self.device):
+            raise ValueError(f"out_u8 must be a contiguous uint8 tensor of shape {(n, H, W, 3)} on {self.device}")
         if out_f32 is None and out_u8 is None:
             raise ValueError("no output requested")
         st = stream or torch.cuda.current_stream(self.device)
@@ -122,7 +132,7 @@ class JpegBatchDecoder:
             _lib.check(self.lib.dsmil_jpeg_decode_batch(
                 self._blob.data_ptr(), pb.blob_bytes, self._hdr.data_ptr(), n, H, W,
                 out_u8.data_ptr() if out_u8 is not None else None,
-                out_f32.data_ptr() if out_f32 is not None else None,
+                out_f32.data_ptr() if out_f32 is not None else None, channels_last,
                 self._status.data_ptr(), ws_ptr, self._ws.numel() - (ws_ptr - self._ws.data_ptr()), st.cuda_stream),
                 "dsmil_jpeg_decode_batch")
         return self._status[:n]

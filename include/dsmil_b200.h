@@ -90,11 +90,16 @@ int dsmil_patches_u8_to_f32(const uint8_t* in, int64_t B, int32_t H, int32_t W, 
  * HW <= 16384. */
 int dsmil_instnorm_act(const float* x, const float* residual, float* y, int64_t planes, int32_t HW, float eps,
                        int32_t relu, void* stream);
+/* The same operator on channels-last memory, [N][HW][C] fp32 (torch.channels_last: the layout in which cuDNN's
+ * convolutions of this backbone run fastest on B200).  C a multiple of 32; statistics per (sample, channel) over HW. */
+int dsmil_instnorm_act_nhwc(const float* x, const float* residual, float* y, int64_t N, int32_t HW, int32_t C, float eps,
+                            int32_t relu, void* stream);
 
 /* Patch loader of the embedding loop on the device (compute_feats.py:26-29 `Image.open(path)` + `VF.to_tensor`,
  * executed by 4 DataLoader workers, compute_feats.py:55): a batch of n JPEG FILES, stored back to back in `blob`
  * (device, blob_bytes long), is decoded to uint8 HWC [n,H,W,3] (== np.asarray(Image.open(f).convert("RGB"))) and / or
- * float32 CHW [n,3,H,W] (== VF.to_tensor of it), bit for bit what PIL's libjpeg produces with its defaults (ISLOW
+ * float32 CHW [n,3,H,W] (== VF.to_tensor of it; with f32_channels_last = 1 the same values in torch.channels_last
+ * memory order [n,H,W,3], the layout the backbone's convolutions run fastest in), bit for bit what PIL's libjpeg produces with its defaults (ISLOW
  * IDCT, fancy upsampling).  `headers` = the n fixed-size records written by dsmil_jpeg_parse_batch of
  * libdsmil_host.so (include/dsmil_host.h), copied to the device; dsmil_jpeg_header_bytes_dev() is their size.
  * Decodable: baseline / extended-sequential Huffman, 8 bit, grey or YCbCr 4:4:4 / 4:2:2 / 4:2:0, one interleaved
@@ -104,8 +109,8 @@ int dsmil_instnorm_act(const float* x, const float* residual, float* y, int64_t 
 int32_t dsmil_jpeg_header_bytes_dev(void);
 int64_t dsmil_jpeg_workspace_bytes(int32_t n, int32_t H, int32_t W, int64_t blob_bytes);
 int dsmil_jpeg_decode_batch(const uint8_t* blob, int64_t blob_bytes, const void* headers, int32_t n, int32_t H, int32_t W,
-                            uint8_t* out_u8, float* out_f32, int32_t* status, void* workspace, int64_t workspace_bytes,
-                            void* stream);
+                            uint8_t* out_u8, float* out_f32, int32_t f32_channels_last, int32_t* status, void* workspace,
+                            int64_t workspace_bytes, void* stream);
 
 /* Live per-kernel timing for the roofline report (bench.py): when enabled, tagged launches are
  * bracketed by CUDA events on the launching stream.  dsmil_profile_read synchronises those events,

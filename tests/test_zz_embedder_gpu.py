@@ -80,3 +80,56 @@ def test_fused_resnet18_matches_untouched_module():
         p.requires_grad = True
     y = fused(x[:2])
     assert y.requires_grad
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 112, 112), (3, 64, 56, 56), (2, 128, 28, 28), (2, 256, 14, 14), (2, 512, 7, 7),
+                                   (1, 32, 3, 5), (2, 96, 1, 2), (1, 2048, 7, 7)])
+@pytest.mark.parametrize("with_res,relu", [(False, True), (True, True), (False, False)])
+def test_instnorm_act_channels_last_matches_torch(shape, with_res, relu):
+    """The NHWC kernel (dsmil_instnorm_act_nhwc): same operator on torch.channels_last memory, layout preserved."""
+    from dsmil_wsi_b200.embedder import instnorm_act
+    g = torch.Generator(device="cuda").manual_seed(sum(shape) + 1)
+    x = (torch.randn(*shape, generator=g, device="cuda") * 3.0 + 40.0).contiguous(memory_format=torch.channels_last)
+    res = torch.randn(*shape, generator=g, device="cuda").contiguous(memory_format=torch.channels_last) if with_res else None
+    want = _ref(x.contiguous(), res.contiguous() if res is not None else None, relu)      # mean 40, std 3: the shifted sums matter
+    got = instnorm_act(x, res, relu)
+    assert got.is_contiguous(memory_format=torch.channels_last)
+    scale = float(want.abs().max().clamp_min(1.0))
+    assert float((got - want).abs().max()) <= 3e-5 * scale, shape
+    x2 = x.clone(memory_format=torch.channels_last)
+    out = instnorm_act(x2, res, relu, out=x2)
+    assert out.data_ptr() == x2.data_ptr() and torch.equal(out, got)
+    # a residual in the other layout is converted, not misread
+    if res is not None:
+        assert torch.equal(instnorm_act(x, res.contiguous(), relu), got)
+
+
+def test_channels_last_with_odd_channel_count_still_correct():
+    from dsmil_wsi_b200.embedder import instnorm_act
+    x = torch.randn(2, 5, 6, 7, device="cuda").contiguous(memory_format=torch.channels_last)
+    want = _ref(x.contiguous(), None, True)
+    assert float((instnorm_act(x, None, True) - want).abs().max()) <= 2e-5
+
+
+def test_fused_resnet18_channels_last_matches_untouched_module():
+    import copy
+    import torchvision.models as models
+    from dsmil_wsi_b200.embedder import fuse_instance_norm
+    torch.manual_seed(0)
+    resnet = models.resnet18(weights=None, norm_layer=torch.nn.InstanceNorm2d)
+    resnet.fc = torch.nn.Identity()
+    for p in resnet.parameters():
+        p.requires_grad = False
+    ref = copy.deepcopy(resnet).cuda().eval()
+    fused = resnet.cuda().eval().to(memory_format=torch.channels_last)
+    assert fuse_instance_norm(fused) == 20
+    x = torch.rand(6, 3, 224, 224, device="cuda")
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            a = ref(x)
+            b = fused(x.contiguous(memory_format=torch.channels_last))
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert float((a - b).abs().max()) <= 2e-4 * float(a.abs().max()), float((a - b).abs().max())

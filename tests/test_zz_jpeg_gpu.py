@@ -45,6 +45,20 @@ def test_reference_patch_batch_128x224_q70():
     _check(jc.patch_files(128))
 
 
+def test_channels_last_float_output_holds_the_same_values():
+    from dsmil_wsi_b200 import jpeg
+    files = jc.patch_files(5, 64, 48)
+    pb = jpeg.parse_batch(files)
+    dec = jpeg.JpegBatchDecoder(DEV)
+    a = torch.empty(5, 3, 64, 48, device=DEV)
+    b = torch.empty(5, 3, 64, 48, device=DEV, memory_format=torch.channels_last)
+    dec.decode(pb, out_f32=a)
+    dec.decode(pb, out_f32=b)
+    torch.cuda.synchronize()
+    assert b.is_contiguous(memory_format=torch.channels_last) and torch.equal(a, b)
+    assert torch.equal(a[0].cpu(), _to_tensor(jc.pil_rgb(files[0])))
+
+
 def test_mixed_tables_grey_and_optimised_in_one_batch():
     img = jc.histology_like(96, 80, 3)
     b = io.BytesIO()
@@ -102,7 +116,7 @@ def test_abi_rejects_bad_arguments():
     need = lib.dsmil_jpeg_workspace_bytes(4, 224, 224, 1000)
     assert need >= 4 * 3 * 224 * 224 * 3
     buf = torch.zeros(4096, dtype=torch.uint8, device=DEV)
-    rc = lib.dsmil_jpeg_decode_batch(buf.data_ptr(), 100, buf.data_ptr(), 1, 8, 8, buf.data_ptr(), None, buf.data_ptr(),
+    rc = lib.dsmil_jpeg_decode_batch(buf.data_ptr(), 100, buf.data_ptr(), 1, 8, 8, buf.data_ptr(), None, 0, buf.data_ptr(),
                                      buf.data_ptr(), 16, None)
     assert rc == -2                                     # DSMIL_ERR_WORKSPACE
 
