@@ -376,7 +376,7 @@ def synth_patch_files(n, seed=0, hw=224, quality=70):
     return out
 
 
-def files_leg(dev, refmod, n_files=1024, batch=128, workers=4):
+def files_leg(dev, refmod, n_files=4096, batch=128, workers=4):
     """(a) the device JPEG loader alone on one 128-patch batch, against PIL on `workers` host threads (the reference's
     DataLoader(num_workers=4)); (b) compute_feats over a bag folder of n_files patches, wall clock, CSV written:
     this repo's loop (device decode / host decode) and the reference's own unmodified compute_feats.compute_feats."""
@@ -416,6 +416,12 @@ def files_leg(dev, refmod, n_files=1024, batch=128, workers=4):
                               "h2d_bytes_device_route": int(pb.blob_bytes + pb.n * jpeg.header_bytes()),
                               "h2d_bytes_reference": batch * 3 * 224 * 224 * 4,
                               "what": "H2D of the files + k_jpeg_entropy/idct/color (CUDA events) vs PIL decode on host threads"}
+    # one launch over 8 batches: the entropy kernel is latency-bound per patch (one warp each), so its time does not grow
+    pb8 = jpeg.parse_batch(distinct * 8, pin=True)
+    x8 = torch.empty(8 * batch, 3, 224, 224, device=dev)
+    ms8 = cuda_time_ms(lambda: dec.decode(pb8, out_f32=x8), 5, warm=2)
+    out["loader_batch1024"] = {"device_ms": ms8, "device_patches_per_s": 8 * batch / (ms8 / 1e3)}
+    del x8, pb8
     # (b) the loop from a folder
     root = tempfile.mkdtemp(prefix="dsmil_files_")
     try:
@@ -425,7 +431,7 @@ def files_leg(dev, refmod, n_files=1024, batch=128, workers=4):
             with open(os.path.join(bag, f"{i // 32}_{i % 32}.jpeg"), "wb") as f:
                 f.write(distinct[i % batch])
         args = types.SimpleNamespace(batch_size=batch, num_workers=workers)
-        ours = make_embedder(mil, dev, True)
+        ours = make_embedder(mil, dev, True)              # embed_bag switches it to channels-last itself
 
         def run(fn, route=None):
             if route is not None:
@@ -467,7 +473,7 @@ def io_lines(text):
     return io.StringIO(text)
 
 
-def make_embedder(modlib, dev, fuse):
+def make_embedder(modlib, dev, fuse, channels_last=False):
     import torchvision.models as models
     torch.manual_seed(0)
     resnet = models.resnet18(weights=None, norm_layer=torch.nn.InstanceNorm2d)    # compute_feats.py:154 (norm_layer='instance')
@@ -478,6 +484,8 @@ def make_embedder(modlib, dev, fuse):
     if fuse:
         from dsmil_wsi_b200.embedder import fuse_instance_norm
         fuse_instance_norm(ic.feature_extractor)
+    if channels_last:                                     # what embed.embed_bag does to the backbone (DSMIL_B200_NHWC)
+        ic.feature_extractor.to(memory_format=torch.channels_last)
     return ic
 
 
@@ -487,16 +495,21 @@ def embed_leg(dev, refmod, batch=128):
     x = torch.rand(batch, 3, 224, 224, generator=g, device=dev)
     out = {"batch": batch, "what": "IClassifier(ResNet-18 with nn.InstanceNorm2d, fc) on a 128 x 3 x 224 x 224 fp32 batch "
                                    "(compute_feats.py:70-76,146-174); convolutions = cuDNN in both arms (TF32 allowed, torch default)"}
-    ours = make_embedder(mil, dev, True)
+    ours = make_embedder(mil, dev, True, channels_last=True)
+    xcl = x.contiguous(memory_format=torch.channels_last)     # the layout the JPEG loader writes the batch in
     with torch.no_grad():
-        ms = cuda_time_ms(lambda: ours(x), 5, warm=2)
-    out.update({"value": batch / (ms / 1e3), "unit": "patches/s", "ms_per_batch": ms,
-                "ours": "convs cuDNN; InstanceNorm + residual + ReLU fused (dsmil_instnorm_act); fc scores by libdsmil_b200"})
+        ms = cuda_time_ms(lambda: ours(xcl), 5, warm=2)
+        ours_nchw = make_embedder(mil, dev, True)
+        ms_nchw = cuda_time_ms(lambda: ours_nchw(x), 5, warm=2)
+        del ours_nchw
+    out.update({"value": batch / (ms / 1e3), "unit": "patches/s", "ms_per_batch": ms, "ms_per_batch_nchw": ms_nchw,
+                "ours": "channels-last: convs cuDNN NHWC; InstanceNorm + residual + ReLU fused (dsmil_instnorm_act_nhwc); fc "
+                        "scores by libdsmil_b200.  ms_per_batch_nchw = the same with NCHW memory (dsmil_instnorm_act)"})
     if refmod is not None:
         ref = make_embedder(refmod, dev, False)
         with torch.no_grad():
             msr = cuda_time_ms(lambda: ref(x), 5, warm=2)
-            fa, fb = ours(x)[0], ref(x)[0]
+            fa, fb = ours(xcl)[0], ref(x)[0]
         out.update({"torch_eager_gpu_ms": msr, "torch_eager_gpu_patches_per_s": batch / (msr / 1e3), "speedup": msr / ms,
                     "max_abs_feature_diff": float((fa - fb).abs().max())})
     return out
@@ -747,9 +760,10 @@ def run_ours(args):
             import dsmil as mil
             from dsmil_wsi_b200.sharded import sharded_forward
             PB, NBATCH = 128, 4                       # 512 patches per rank per slide
-            ic = make_embedder(mil, dev, True)
+            ic = make_embedder(mil, dev, True, channels_last=True)
             gen = torch.Generator(device=dev).manual_seed(50 + rank)
-            px = [torch.rand(PB, 3, 224, 224, generator=gen, device=dev) for _ in range(NBATCH)]
+            px = [torch.rand(PB, 3, 224, 224, generator=gen, device=dev).contiguous(memory_format=torch.channels_last)
+                  for _ in range(NBATCH)]
             sops = CudaShardOps(milnet_params(net)) if world > 1 else None
 
             def slide():
@@ -773,7 +787,7 @@ def run_ours(args):
             tms = float(tms.item())
             embed_agg = {"value": PB * NBATCH * world / (tms / 1e3), "unit": "patches/s", "ms_per_slide": tms,
                          "slides_per_s": 1e3 / tms, "patches_per_rank": PB * NBATCH, "n_gpus": world, "scaling": "weak",
-                         "what": "per slide: each rank embeds its 512 patches (ResNet-18-InstanceNorm, fused norm kernel) and the "
+                         "what": "per slide: each rank embeds its 512 patches (ResNet-18-InstanceNorm, channels-last, fused norm kernel) and the "
                                  "features go straight into the row-sharded DSMIL aggregator (NCCL: candidates + partial sums)"}
             del px, ic
         except Exception as e:

@@ -18,6 +18,8 @@ SIGNATURES = {
     "dsmil_jpeg_header_bytes": (C.c_int32, []),
     "dsmil_jpeg_parse": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
     "dsmil_jpeg_parse_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "dsmil_files_offsets": (C.c_int64, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "dsmil_files_read": (C.c_int64, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
 }
 ERRORS = {-1: "bad argument", -2: "I/O error", -3: "ragged row (field count differs from the header)",
           -4: "field is not a number", -5: "output buffer too small"}

@@ -76,8 +76,8 @@ def build_host_library(force=False):
     cc = os.environ.get("CC") or shutil.which("gcc") or shutil.which("cc")
     if not cc:
         raise RuntimeError("no C compiler found (set CC=/path/to/gcc)")
-    cmd = [cc, "-O3", "-std=c11", "-Wall", "-Wextra", "-shared", "-fPIC", "-o", HOST_LIB] + \
-          [os.path.join(HOST_CSRC, s) for s in HOST_SOURCES] + ["-lm"]
+    cmd = [cc, "-O3", "-std=c11", "-D_POSIX_C_SOURCE=200809L", "-Wall", "-Wextra", "-shared", "-fPIC", "-o", HOST_LIB] + \
+          [os.path.join(HOST_CSRC, s) for s in HOST_SOURCES] + ["-lm", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

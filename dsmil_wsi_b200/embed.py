@@ -24,6 +24,7 @@ from __future__ import annotations
 import glob
 import os
 import sys
+import weakref
 from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, List, Optional, Sequence
 
@@ -179,10 +180,67 @@ def jpeg_route() -> str:
     return r
 
 
+class _GraphedEmbedder:
+    """The embedder forward of one full batch as a CUDA graph: ~70 launches (cuDNN convolutions, the fused norm kernels,
+    the score kernel) become one replay, so the loop is paced by the GPU, not by the host thread that also stages the
+    next batch.  The static input is this object's own buffer (one device copy per batch); outputs are cloned out."""
+
+    def __init__(self, i_classifier, batch, H, W, dev, fmt):
+        self.key = self.make_key(i_classifier, batch, H, W, dev, fmt)
+        self.x = torch.zeros(batch, 3, H, W, dtype=torch.float32, device=dev).contiguous(memory_format=fmt)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                i_classifier(self.x)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.feats, self.classes = i_classifier(self.x)
+
+    @staticmethod
+    def make_key(i_classifier, batch, H, W, dev, fmt):
+        # replaced parameter tensors (not in-place updates) invalidate a captured graph: key on their addresses
+        return (batch, H, W, str(dev), str(fmt), tuple(p.data_ptr() for p in i_classifier.parameters()),
+                tuple(b.data_ptr() for b in i_classifier.buffers()))
+
+    def __call__(self, x):
+        self.x.copy_(x)
+        self.graph.replay()
+        return self.feats.clone(), self.classes.clone()
+
+
+_GRAPHS = weakref.WeakKeyDictionary()      # model -> (key, _GraphedEmbedder or None); kept off the module itself so that
+                                            # deepcopy / pickling of the caller's model never meets a CUDA graph
+
+
+def _graphed(i_classifier, batch, H, W, dev, fmt):
+    """The cached graph of this (model, geometry), captured on first use; None when capture is not possible."""
+    key = _GraphedEmbedder.make_key(i_classifier, batch, H, W, dev, fmt)
+    cur = _GRAPHS.get(i_classifier)
+    if cur is not None and cur[0] == key:
+        return cur[1]
+    try:
+        g = _GraphedEmbedder(i_classifier, batch, H, W, dev, fmt)
+    except Exception as e:                                   # a backbone with capture-hostile ops: run it eagerly
+        sys.stderr.write(f"[dsmil_b200] embedder forward not captured as a CUDA graph ({type(e).__name__}: {e}); "
+                         "running it eagerly\n")
+        torch.cuda.synchronize(dev)
+        g = None
+    _GRAPHS[i_classifier] = (key, g)
+    return g
+
+
 @torch.no_grad()
 def embed_bag(paths: Sequence[str], i_classifier, batch_size: int = 128, num_workers: int = 4,
               device: Optional[torch.device] = None):
-    """Features [N, D] (device) and instance scores [N, C] (device) of one bag of patch files."""
+    """Features [N, D] (device) and instance scores [N, C] (device) of one bag of patch files.
+
+    Three things run concurrently per batch: a staging thread reads + parses the NEXT batch's files natively and
+    enqueues its H2D copy and decode kernels on a side stream; the GPU decodes that batch under the backbone of the
+    CURRENT one; the calling thread only replays the backbone's CUDA graph (DSMIL_B200_EMBED_GRAPH=0: launches it
+    eagerly) and collects the features."""
     from . import jpeg
     dev = device or next(i_classifier.parameters()).device
     if dev.type != "cuda":
@@ -205,71 +263,74 @@ def embed_bag(paths: Sequence[str], i_classifier, batch_size: int = 128, num_wor
     route = jpeg_route()
     first = _decode_u8(paths[0])
     H, W = first.shape[:2]
+    batches = [paths[i:i + batch_size] for i in range(0, len(paths), batch_size)]
+    full_batches = sum(1 for b in batches if len(b) == batch_size)
     feats_out, cls_out = [], []
-    with torch.cuda.device(dev), ThreadPoolExecutor(max_workers=max(1, num_workers)) as pool:
-        st = _Staging(batch_size, H, W, dev, fmt)
-        compute = torch.cuda.current_stream()
-        for s in range(2):
-            st.consumed[s].record(compute)
-            st.copied[s].record(st.stream)
-        batches = [paths[i:i + batch_size] for i in range(0, len(paths), batch_size)]
-
-        def stage(bi):
-            s = bi % 2
-            names = batches[bi]
-            n = len(names)
-            on_device = False
-            files = None
-            if route != "host":
-                files = list(pool.map(_read_file, names))
-                st.copied[s].synchronize()                  # the pinned blob / headers of this slot are free again
-                st.check_status(s)
-                pb = jpeg.parse_batch(files, st.blob[s], st.hdr[s], pin=True)
-                on_device = pb.bad == 0 and (pb.H, pb.W) == (H, W)
-                if not on_device and route == "gpu":
-                    raise RuntimeError(f"DSMIL_B200_JPEG=gpu, but {pb.bad} file(s) of the batch starting at {names[0]} "
-                                       f"are not decodable on the device (statuses {pb.statuses.tolist()})")
-            st.consumed[s].synchronize()                    # the previous user of this slot's device buffers has read them
-            if on_device:
-                out = st.f32(s)
-                st.stream.wait_event(st.consumed[s])
-                status = st.decoder.decode(pb, out_f32=out[:n], stream=st.stream)
-                with torch.cuda.stream(st.stream):
-                    st.status_host[s][:n].copy_(status, non_blocking=True)
-                    st.copied[s].record(st.stream)
-                st.status_names[s] = names
-                return s, n, True
-            imgs = list(pool.map(_decode_u8, files if files is not None else names))
-            hb, db = st.u8(s)
-            st.copied[s].synchronize()
-            for j, im in enumerate(imgs):
-                if im.shape != (H, W, 3):
-                    raise ValueError(f"patch {names[j]} is {im.shape}, expected {(H, W, 3)}")
-                hb[j].copy_(torch.from_numpy(im))
-            with torch.cuda.stream(st.stream):
-                db[:n].copy_(hb[:n], non_blocking=True)
-                st.copied[s].record(st.stream)
-            return s, n, False
-
-        pending = stage(0)
-        for bi in range(len(batches)):
-            s, n, on_device = pending
-            compute.wait_event(st.copied[s])
-            if on_device:
-                x = st.f32(s)[:n]
-            else:
-                x = patches_to_float(st.dev_u8[s][:n]).contiguous(memory_format=fmt)
+    with torch.cuda.device(dev):
+        graphed = None
+        if os.environ.get("DSMIL_B200_EMBED_GRAPH", "1") != "0" and full_batches >= 4:
+            graphed = _graphed(i_classifier, batch_size, H, W, dev, fmt)     # before any other thread touches CUDA
+        with ThreadPoolExecutor(max_workers=max(1, num_workers)) as pool, ThreadPoolExecutor(max_workers=1) as stager:
+            st = _Staging(batch_size, H, W, dev, fmt)
+            compute = torch.cuda.current_stream()
+            for s in range(2):
                 st.consumed[s].record(compute)
-            if bi + 1 < len(batches):
-                pending = stage(bi + 1)                     # overlaps with the backbone of this batch
-            feats, classes = i_classifier(x)
-            if on_device:
-                st.consumed[s].record(compute)              # the backbone has read the decoded batch in place
-            feats_out.append(feats)
-            cls_out.append(classes)
-        for s in range(2):
-            st.copied[s].synchronize()
-            st.check_status(s)
+                st.copied[s].record(st.stream)
+
+            def stage(bi):                                  # runs on the staging thread
+                s = bi % 2
+                names = batches[bi]
+                n = len(names)
+                on_device = False
+                pb = None
+                with torch.cuda.device(dev):
+                    if route != "host":
+                        st.copied[s].synchronize()          # the pinned blob / headers of this slot are free again
+                        st.check_status(s)
+                        pb = jpeg.parse_paths(names, st.blob[s], st.hdr[s], pin=True, threads=max(1, num_workers))
+                        on_device = pb.bad == 0 and (pb.H, pb.W) == (H, W)
+                        if not on_device and route == "gpu":
+                            raise RuntimeError(f"DSMIL_B200_JPEG=gpu, but {pb.bad} file(s) of the batch starting at {names[0]} "
+                                               f"are not decodable on the device (statuses {pb.statuses.tolist()})")
+                    st.consumed[s].synchronize()            # the previous user of this slot's device buffers has read them
+                    if on_device:
+                        out = st.f32(s)
+                        status = st.decoder.decode(pb, out_f32=out[:n], stream=st.stream)
+                        with torch.cuda.stream(st.stream):
+                            st.status_host[s][:n].copy_(status, non_blocking=True)
+                            st.copied[s].record(st.stream)
+                        st.status_names[s] = names
+                        return s, n, True
+                    srcs = [pb.file_bytes(j) for j in range(n)] if pb is not None else names
+                    imgs = list(pool.map(_decode_u8, srcs))
+                    hb, db = st.u8(s)
+                    st.copied[s].synchronize()
+                    for j, im in enumerate(imgs):
+                        if im.shape != (H, W, 3):
+                            raise ValueError(f"patch {names[j]} is {im.shape}, expected {(H, W, 3)}")
+                        hb[j].copy_(torch.from_numpy(im))
+                    with torch.cuda.stream(st.stream):
+                        db[:n].copy_(hb[:n], non_blocking=True)
+                        st.copied[s].record(st.stream)
+                    return s, n, False
+
+            pending = stager.submit(stage, 0)
+            for bi in range(len(batches)):
+                s, n, on_device = pending.result()
+                if bi + 1 < len(batches):
+                    pending = stager.submit(stage, bi + 1)  # read / parse / copy / decode the next batch meanwhile
+                compute.wait_event(st.copied[s])
+                x = st.f32(s)[:n] if on_device else patches_to_float(st.dev_u8[s][:n]).contiguous(memory_format=fmt)
+                if graphed is not None and n == batch_size:
+                    feats, classes = graphed(x)             # copies x into the graph's input first
+                else:
+                    feats, classes = i_classifier(x)
+                st.consumed[s].record(compute)              # the slot's device buffers have been read
+                feats_out.append(feats)
+                cls_out.append(classes)
+            for s in range(2):
+                st.copied[s].synchronize()
+                st.check_status(s)
     return torch.cat(feats_out), torch.cat(cls_out)
 
 

@@ -32,6 +32,10 @@ class ParsedBatch:
         self.n, self.blob, self.blob_bytes, self.headers, self.offsets = n, blob, blob_bytes, headers, offsets
         self.bad, self.H, self.W, self.statuses = bad, H, W, statuses
 
+    def file_bytes(self, i: int) -> bytes:
+        """The bytes of file i (for a decoder outside the device path)."""
+        return self.blob.numpy()[int(self.offsets[i]):int(self.offsets[i + 1])].tobytes()
+
 
 class _Pinned:
     """A growable pinned byte buffer (re-pinning is expensive: grow geometrically, reuse across batches)."""
@@ -47,20 +51,10 @@ class _Pinned:
         return self.t
 
 
-def parse_batch(files: Sequence[bytes], blob_buf: Optional[_Pinned] = None, hdr_buf: Optional[_Pinned] = None,
-                pin: bool = False) -> ParsedBatch:
-    """Concatenates the files into one (optionally pinned) buffer and parses their headers on the host."""
+def _parse_blob(blob: torch.Tensor, total: int, offsets: np.ndarray, n: int, hdr_buf: Optional[_Pinned], pin: bool
+                ) -> ParsedBatch:
     lib = _hostlib.load()
     hb = header_bytes()
-    n = len(files)
-    sizes = np.fromiter((len(f) for f in files), dtype=np.int64, count=n)
-    offsets = np.zeros(n + 1, dtype=np.int64)
-    np.cumsum(sizes, out=offsets[1:])
-    total = int(offsets[-1])
-    blob = (blob_buf or _Pinned()).get(total + 16, pin)
-    view = blob.numpy()
-    for i, f in enumerate(files):
-        view[offsets[i]:offsets[i + 1]] = np.frombuffer(f, dtype=np.uint8)
     headers = (hdr_buf or _Pinned()).get(max(n, 1) * hb, pin)
     bad = int(lib.dsmil_jpeg_parse_batch(blob.data_ptr(), offsets.ctypes.data, n, headers.data_ptr())) if n else 0
     if bad < 0:
@@ -74,6 +68,42 @@ def parse_batch(files: Sequence[bytes], blob_buf: Optional[_Pinned] = None, hdr_
     if n and bad == 0 and (np.any(widths != W) or np.any(heights != H)):
         bad = int(np.sum((widths != W) | (heights != H)))
     return ParsedBatch(n, blob, total, headers, offsets, bad, H, W, statuses.copy())
+
+
+def parse_batch(files: Sequence[bytes], blob_buf: Optional[_Pinned] = None, hdr_buf: Optional[_Pinned] = None,
+                pin: bool = False) -> ParsedBatch:
+    """Concatenates the files (bytes objects) into one (optionally pinned) buffer and parses their headers."""
+    n = len(files)
+    sizes = np.fromiter((len(f) for f in files), dtype=np.int64, count=n)
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    total = int(offsets[-1])
+    blob = (blob_buf or _Pinned()).get(total + 16, pin)
+    view = blob.numpy()
+    for i, f in enumerate(files):
+        view[offsets[i]:offsets[i + 1]] = np.frombuffer(f, dtype=np.uint8)
+    return _parse_blob(blob, total, offsets, n, hdr_buf, pin)
+
+
+def parse_paths(paths: Sequence[str], blob_buf: Optional[_Pinned] = None, hdr_buf: Optional[_Pinned] = None,
+                pin: bool = False, threads: int = 4) -> ParsedBatch:
+    """Reads the files natively (libdsmil_host.so, `threads` reader threads, the GIL released) straight into the
+    (optionally pinned) blob and parses their headers: no per-file Python objects."""
+    import ctypes as C
+    import os
+    lib = _hostlib.load()
+    n = len(paths)
+    arr = (C.c_char_p * max(n, 1))(*[os.fsencode(p) for p in paths])
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    rc = int(lib.dsmil_files_offsets(arr, n, offsets.ctypes.data))
+    if rc < 0:
+        raise FileNotFoundError(f"cannot stat patch file {paths[-rc - 1]}")
+    total = int(offsets[-1])
+    blob = (blob_buf or _Pinned()).get(total + 16, pin)
+    rc = int(lib.dsmil_files_read(arr, n, offsets.ctypes.data, blob.data_ptr(), int(threads)))
+    if rc < 0:
+        raise OSError(f"cannot read patch file {paths[-rc - 1]}")
+    return _parse_blob(blob, total, offsets, n, hdr_buf, pin)
 
 
 class JpegBatchDecoder:

@@ -39,6 +39,13 @@ int32_t dsmil_jpeg_header_bytes(void);
 int32_t dsmil_jpeg_parse(const uint8_t* file, int64_t len, void* header);
 int32_t dsmil_jpeg_parse_batch(const uint8_t* blob, const int64_t* offsets, int32_t n, void* headers);
 
+/* File reader of the loader: n files (NUL-terminated paths) straight into one caller buffer (normally pinned, the
+ * source of the H2D copy).  dsmil_files_offsets: offsets[0..n] = prefix sums of the file sizes; dsmil_files_read:
+ * file i -> blob[offsets[i], offsets[i+1]) with `threads` (1..16) reader threads.  Return 0, or -(i+1) when file i
+ * cannot be stat'ed / read completely. */
+int64_t dsmil_files_offsets(const char* const* paths, int32_t n, int64_t* offsets);
+int64_t dsmil_files_read(const char* const* paths, int32_t n, const int64_t* offsets, uint8_t* blob, int32_t threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,3 +75,22 @@ def test_parse_flags_what_the_device_path_does_not_take():
 def test_parse_empty_batch():
     pb = _parse([])
     assert pb.n == 0 and pb.bad == 0
+
+
+def test_parse_paths_reads_files_natively(tmp_path):
+    from dsmil_wsi_b200 import jpeg
+    files = jc.patch_files(9, 48, 40)
+    names = []
+    for i, data in enumerate(files):
+        p = tmp_path / f"{i}_{i}.jpeg"
+        p.write_bytes(data)
+        names.append(str(p))
+    for threads in (1, 3, 16):
+        pb = jpeg.parse_paths(names, threads=threads)
+        ref = jpeg.parse_batch(files)
+        assert pb.bad == 0 and (pb.H, pb.W) == (48, 40) and pb.offsets.tolist() == ref.offsets.tolist()
+        assert bytes(pb.blob.numpy()[:pb.blob_bytes]) == b"".join(files)
+        assert pb.file_bytes(4) == files[4]
+    with pytest.raises(FileNotFoundError):
+        jpeg.parse_paths(names[:2] + [str(tmp_path / "missing.jpeg")])
+    assert jpeg.parse_paths([]).n == 0

@@ -171,3 +171,32 @@ def test_embed_bag_auto_route_falls_to_pil_for_a_progressive_patch(tmp_path, mon
     monkeypatch.setenv("DSMIL_B200_JPEG", "gpu")
     with pytest.raises(RuntimeError, match="not decodable on the device"):
         embed.embed_bag(paths, ic, batch_size=4, num_workers=2)
+
+
+def test_embed_bag_graph_replay_equals_eager_launches(tmp_path, monkeypatch):
+    """Full batches go through one CUDA-graph replay of the embedder, the ragged tail eagerly: same features."""
+    import torchvision.models as models
+    import dsmil as mil
+    from dsmil_wsi_b200 import embed
+    bag = _write_bag(tmp_path, 70, h=64, w=64)          # 4 full batches of 16 + 6
+    torch.manual_seed(0)
+    resnet = models.resnet18(weights=None, norm_layer=torch.nn.InstanceNorm2d)
+    resnet.fc = torch.nn.Identity()
+    ic = mil.IClassifier(resnet, 512, 2).to(DEV).eval()
+    paths = embed.list_patches(bag)
+    monkeypatch.setenv("DSMIL_B200_EMBED_GRAPH", "1")
+    f_g, c_g = embed.embed_bag(paths, ic, batch_size=16, num_workers=2)
+    assert embed._GRAPHS.get(ic) is not None and embed._GRAPHS[ic][1] is not None, "the embedder was not captured"
+    f_g2, _ = embed.embed_bag(paths, ic, batch_size=16, num_workers=2)          # cached graph, second bag
+    monkeypatch.setenv("DSMIL_B200_EMBED_GRAPH", "0")
+    f_e, c_e = embed.embed_bag(paths, ic, batch_size=16, num_workers=2)
+    assert f_g.shape == (70, 512)
+    assert torch.equal(f_g, f_g2)
+    assert torch.allclose(f_g, f_e, rtol=0, atol=1e-5) and torch.allclose(c_g, c_e, rtol=0, atol=1e-5)
+    # new parameter tensors (e.g. a checkpoint loaded by re-assignment) invalidate the capture
+    ic.fc.weight = torch.nn.Parameter(ic.fc.weight.detach().clone() * 2.0)
+    monkeypatch.setenv("DSMIL_B200_EMBED_GRAPH", "1")
+    _, c_new = embed.embed_bag(paths, ic, batch_size=16, num_workers=2)
+    monkeypatch.setenv("DSMIL_B200_EMBED_GRAPH", "0")
+    _, c_new_e = embed.embed_bag(paths, ic, batch_size=16, num_workers=2)
+    assert torch.allclose(c_new, c_new_e, rtol=0, atol=1e-5) and not torch.allclose(c_new, c_g)
