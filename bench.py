@@ -376,7 +376,7 @@ def synth_patch_files(n, seed=0, hw=224, quality=70):
     return out
 
 
-def files_leg(dev, refmod, n_files=4096, batch=128, workers=4):
+def files_leg(dev, refmod, n_files=4096, batch=128, workers=4, n_bags=2):
     """(a) the device JPEG loader alone on one 128-patch batch, against PIL on `workers` host threads (the reference's
     DataLoader(num_workers=4)); (b) compute_feats over a bag folder of n_files patches, wall clock, CSV written:
     this repo's loop (device decode / host decode) and the reference's own unmodified compute_feats.compute_feats."""
@@ -388,7 +388,7 @@ def files_leg(dev, refmod, n_files=4096, batch=128, workers=4):
     from dsmil_wsi_b200 import embed, jpeg
     from oracle import stage_ref
     distinct = synth_patch_files(batch, seed=5)
-    out = {"what": f"{n_files} patch files (224 x 224 JPEG, quality 70, PIL defaults; {batch} distinct images), batch {batch}, "
+    out = {"what": f"{n_files} patch files in {n_bags} bag folders (224 x 224 JPEG, quality 70, PIL defaults; {batch} distinct images), batch {batch}, "
                    f"{workers} loader workers, ResNet-18-InstanceNorm embedder, '%.4f' CSV written",
            "bytes_per_file": int(np.mean([len(f) for f in distinct]))}
     # (a) loader alone
@@ -425,11 +425,12 @@ def files_leg(dev, refmod, n_files=4096, batch=128, workers=4):
     # (b) the loop from a folder
     root = tempfile.mkdtemp(prefix="dsmil_files_")
     try:
-        bag = os.path.join(root, "in", "class0", "bag0")
-        os.makedirs(bag)
-        for i in range(n_files):
-            with open(os.path.join(bag, f"{i // 32}_{i % 32}.jpeg"), "wb") as f:
-                f.write(distinct[i % batch])
+        bags = [os.path.join(root, "in", "class0", f"bag{b}") for b in range(n_bags)]
+        for b, bag in enumerate(bags):
+            os.makedirs(bag)
+            for i in range(n_files // n_bags):
+                with open(os.path.join(bag, f"{i // 32}_{i % 32}.jpeg"), "wb") as f:
+                    f.write(distinct[(i + 7 * b) % batch])
         args = types.SimpleNamespace(batch_size=batch, num_workers=workers)
         ours = make_embedder(mil, dev, True)              # embed_bag switches it to channels-last itself
 
@@ -446,14 +447,14 @@ def files_leg(dev, refmod, n_files=4096, batch=128, workers=4):
                 best = time.perf_counter() - t0
             os.environ.pop("DSMIL_B200_JPEG", None)
             return best
-        t_dev = run(lambda sp: embed.compute_feats(args, [bag], ours, sp), "gpu")
-        t_host = run(lambda sp: embed.compute_feats(args, [bag], ours, sp), "host")
+        t_dev = run(lambda sp: embed.compute_feats(args, bags, ours, sp), "gpu")
+        t_host = run(lambda sp: embed.compute_feats(args, bags, ours, sp), "host")
         out["compute_feats"] = {"value": n_files / t_dev, "unit": "patches/s", "seconds": t_dev,
                                 "host_decode_route_patches_per_s": n_files / t_host, "host_decode_route_seconds": t_host}
         rcf = stage_ref.load_reference_compute_feats()
         if rcf is not None and refmod is not None:
             ref = make_embedder(refmod, dev, False)
-            t_ref = run(lambda sp: rcf.compute_feats(args, [bag], ref, sp, "single"))
+            t_ref = run(lambda sp: rcf.compute_feats(args, bags, ref, sp, "single"))
             out["compute_feats"].update({"reference_patches_per_s": n_files / t_ref, "reference_seconds": t_ref,
                                          "speedup": t_ref / t_dev,
                                          "reference": "oracle/_ref/compute_feats.py compute_feats (unmodified): DataLoader workers + PIL "

@@ -412,18 +412,23 @@ def compute_feats(args, bags_list, i_classifier, save_path=None, magnification="
     if wire not in ("csv", "bin", "both"):
         raise ValueError(f"wire must be 'csv', 'bin' or 'both', got {wire!r}")
     num_bags = len(bags_list)
-    for i, bag_dir in enumerate(bags_list):
-        paths = list_patches(bag_dir, magnification)
-        feats, classes = embed_bag(paths, i_classifier, getattr(args, "batch_size", 128), getattr(args, "num_workers", 4))
-        sys.stdout.write("\r Computed: {}/{}".format(i + 1, num_bags))
-        if feats is None:
-            print("No valid patch extracted from: " + bag_dir)   # compute_feats.py:77-78
-            continue
-        if sink is not None:
-            sink(bag_dir, feats, classes)
-        if save_path is not None:
-            host = feats.cpu().numpy()
-            if wire in ("csv", "both"):
-                write_bag_csv(host, save_path, bag_dir)
-            if wire in ("bin", "both"):
-                write_bag_container(host, save_path, bag_dir)
+    # the text of bag i is formatted and written (native code, GIL released) while bag i+1 is being embedded
+    with ThreadPoolExecutor(max_workers=1) as writer:
+        written = []
+        for i, bag_dir in enumerate(bags_list):
+            paths = list_patches(bag_dir, magnification)
+            feats, classes = embed_bag(paths, i_classifier, getattr(args, "batch_size", 128), getattr(args, "num_workers", 4))
+            sys.stdout.write("\r Computed: {}/{}".format(i + 1, num_bags))
+            if feats is None:
+                print("No valid patch extracted from: " + bag_dir)   # compute_feats.py:77-78
+                continue
+            if sink is not None:
+                sink(bag_dir, feats, classes)
+            if save_path is not None:
+                host = feats.cpu().numpy()
+                if wire in ("csv", "both"):
+                    written.append(writer.submit(write_bag_csv, host, save_path, bag_dir))
+                if wire in ("bin", "both"):
+                    written.append(writer.submit(write_bag_container, host, save_path, bag_dir))
+        for w in written:
+            w.result()                                       # surfaces I/O errors; every file is on disk on return
