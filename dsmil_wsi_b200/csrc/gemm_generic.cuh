@@ -112,8 +112,12 @@ inline int launch_linear(const float* X, int64_t N, int K, const float* W, const
 }
 
 // ---- out[M1,M2] = sum_n P[n,M1] * R[n,M2]  (reduction over rows; split over grid.z into partials)
-constexpr int TBM = 64, TBK = 16;
-__global__ void __launch_bounds__(256)
+// The weight-gradient GEMMs of the backward (gW1 = dz1^T X is 2 GFLOP at N = 15 000).  128 x 128 output tile per CTA,
+// 8 x 8 per thread: 64 FMAs per four 16-byte shared-memory loads, so the FMA pipe, not the LSU, is the limiter (the
+// former 64 x 64 / 4 x 4 tile was shared-memory-bound at half the FMA rate); the next k-tile is fetched into registers
+// while the current one is multiplied.
+constexpr int TBM = 128, TBK = 16;
+__global__ void __launch_bounds__(256, 2)
 k_gemm_tn(const float* __restrict__ P, int M1, const float* __restrict__ R, int M2, int64_t N,
           int64_t rows_per_split, float* __restrict__ part) {
   __shared__ __align__(16) float Ps[TBK][TBM + 4];
@@ -122,48 +126,125 @@ k_gemm_tn(const float* __restrict__ P, int M1, const float* __restrict__ R, int 
   const int a0 = blockIdx.y * TBM, b0 = blockIdx.x * TBM;
   const int64_t nb = static_cast<int64_t>(blockIdx.z) * rows_per_split;
   const int64_t ne = min(N, nb + rows_per_split);
-  float acc[4][4];
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  // loader role: k-row (tid >> 4) of the tile, columns (tid & 15) * 4 .. + 3 and + 64
   const int ln = tid >> 4, lq = (tid & 15) * 4;
-  for (int64_t n0 = nb; n0 < ne; n0 += TBK) {
+  const bool pvec = (M1 & 3) == 0, rvec = (M2 & 3) == 0;
+  float4 pf[2], rf[2];
+  auto fetch = [&](int64_t n0) {
     const int64_t n = n0 + ln;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float pv = 0.f, rv = 0.f;
+    for (int h = 0; h < 2; ++h) {
+      const int ca = a0 + lq + 64 * h, cb = b0 + lq + 64 * h;
+      float4 pv = make_float4(0.f, 0.f, 0.f, 0.f), rv = pv;
       if (n < ne) {
-        if (a0 + lq + i < M1) pv = __ldg(P + n * M1 + a0 + lq + i);
-        if (b0 + lq + i < M2) rv = __ldg(R + n * M2 + b0 + lq + i);
+        const float* pp = P + n * M1 + ca;
+        const float* rp = R + n * M2 + cb;
+        if (pvec && ca + 3 < M1) pv = __ldg(reinterpret_cast<const float4*>(pp));
+        else {
+          if (ca < M1) pv.x = __ldg(pp);
+          if (ca + 1 < M1) pv.y = __ldg(pp + 1);
+          if (ca + 2 < M1) pv.z = __ldg(pp + 2);
+          if (ca + 3 < M1) pv.w = __ldg(pp + 3);
+        }
+        if (rvec && cb + 3 < M2) rv = __ldg(reinterpret_cast<const float4*>(rp));
+        else {
+          if (cb < M2) rv.x = __ldg(rp);
+          if (cb + 1 < M2) rv.y = __ldg(rp + 1);
+          if (cb + 2 < M2) rv.z = __ldg(rp + 2);
+          if (cb + 3 < M2) rv.w = __ldg(rp + 3);
+        }
       }
-      Ps[ln][lq + i] = pv;
-      Rs[ln][lq + i] = rv;
+      pf[h] = pv;
+      rf[h] = rv;
+    }
+  };
+  if (nb < ne) fetch(nb);
+  for (int64_t n0 = nb; n0 < ne; n0 += TBK) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      *reinterpret_cast<float4*>(&Ps[ln][lq + 64 * h]) = pf[h];
+      *reinterpret_cast<float4*>(&Rs[ln][lq + 64 * h]) = rf[h];
     }
     __syncthreads();
+    if (n0 + TBK < ne) fetch(n0 + TBK);
 #pragma unroll
     for (int kk = 0; kk < TBK; ++kk) {
-      const float4 a = *reinterpret_cast<const float4*>(&Ps[kk][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Rs[kk][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-      const float bv[4] = {b.x, b.y, b.z, b.w};
+      const float4 a_lo = *reinterpret_cast<const float4*>(&Ps[kk][ty * 4]);
+      const float4 a_hi = *reinterpret_cast<const float4*>(&Ps[kk][ty * 4 + 64]);
+      const float4 b_lo = *reinterpret_cast<const float4*>(&Rs[kk][tx * 4]);
+      const float4 b_hi = *reinterpret_cast<const float4*>(&Rs[kk][tx * 4 + 64]);
+      const float av[8] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
+      const float bv[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
   float* out = part + static_cast<int64_t>(blockIdx.z) * M1 * M2;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int a = a0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int a = a0 + ty * 4 + (i & 3) + 64 * (i >> 2);
     if (a >= M1) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int b = b0 + tx * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int b = b0 + tx * 4 + (j & 3) + 64 * (j >> 2);
       if (b < M2) out[static_cast<int64_t>(a) * M2 + b] = acc[i][j];
     }
+  }
+}
+
+// The same product for a handful of left columns (M1 <= 4: the per-class gradients gWi = d_classes^T X and
+// dq_max = dL^T Q): 2 * M1 FLOP per element of R, i.e. a pure stream over R.  Thread = one float4 column group of R,
+// 256 / (M2 / 4) rows in flight per CTA; partial per CTA, combined in a fixed order.
+constexpr int kGemvMaxM1 = 4;
+template <int M1>
+__global__ void __launch_bounds__(256)
+k_gemv_tn(const float* __restrict__ P, const float* __restrict__ R, int M2, int64_t N, int64_t rows_per_split,
+          float* __restrict__ part) {
+  __shared__ float s_acc[256][4 * M1 + 1];
+  const int G = M2 >> 2;                    // float4 groups per row (<= 256)
+  const int rpi = 256 / G;                  // rows per iteration
+  const int g = threadIdx.x % G, ro = threadIdx.x / G;
+  const int64_t nb = static_cast<int64_t>(blockIdx.x) * rows_per_split;
+  const int64_t ne = min(N, nb + rows_per_split);
+  float acc[M1][4];
+#pragma unroll
+  for (int c = 0; c < M1; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+  if (ro < rpi) {
+#pragma unroll 4
+    for (int64_t n = nb + ro; n < ne; n += rpi) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(R + n * M2) + g);
+#pragma unroll
+      for (int c = 0; c < M1; ++c) {
+        const float pv = __ldg(P + n * M1 + c);
+        acc[c][0] = fmaf(pv, r.x, acc[c][0]); acc[c][1] = fmaf(pv, r.y, acc[c][1]);
+        acc[c][2] = fmaf(pv, r.z, acc[c][2]); acc[c][3] = fmaf(pv, r.w, acc[c][3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < M1; ++c)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s_acc[threadIdx.x][4 * c + q] = acc[c][q];
+  __syncthreads();
+  // thread (g, ro == 0) adds the other row groups in order, then writes its 4 * M1 values
+  if (ro == 0) {
+    for (int r2 = 1; r2 < rpi; ++r2)
+#pragma unroll
+      for (int c = 0; c < M1; ++c)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[c][q] += s_acc[r2 * G + g][4 * c + q];
+    float* out = part + static_cast<int64_t>(blockIdx.x) * M1 * M2;
+#pragma unroll
+    for (int c = 0; c < M1; ++c)
+      *reinterpret_cast<float4*>(out + static_cast<int64_t>(c) * M2 + 4 * g) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
   }
 }
 
@@ -179,20 +260,48 @@ k_colsum(const float* __restrict__ P, int M, int64_t N, int64_t rows_per_split, 
   }
 }
 
-// out[i] = sum_z part[z][i]  (fixed order)
+// out[i] = sum_z part[z][i]  (fixed order: warp w of the CTA adds z = w, w + 8, ... with four independent running sums,
+// the eight warp sums are then added in warp order).  32 outputs per CTA, so a short vector (a bias gradient: 128
+// values from 235 partials) is no longer one CTA walking 235 dependent steps.
 __global__ void __launch_bounds__(256)
 k_sum_partials(const float* __restrict__ part, int S, int64_t L, float* __restrict__ out) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= L) return;
-  float s = 0.f;
-  for (int z = 0; z < S; ++z) s += part[static_cast<int64_t>(z) * L + i];
-  out[i] = s;
+  __shared__ float s_w[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 32 + lane;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (i < L) {
+    int z = w;
+    for (; z + 24 < S; z += 32) {
+      s0 += part[static_cast<int64_t>(z) * L + i];
+      s1 += part[static_cast<int64_t>(z + 8) * L + i];
+      s2 += part[static_cast<int64_t>(z + 16) * L + i];
+      s3 += part[static_cast<int64_t>(z + 24) * L + i];
+    }
+    for (; z < S; z += 8) s0 += part[static_cast<int64_t>(z) * L + i];
+  }
+  s_w[w][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (w == 0 && i < L)
+    out[i] = ((s_w[0][lane] + s_w[1][lane]) + (s_w[2][lane] + s_w[3][lane])) +
+             ((s_w[4][lane] + s_w[5][lane]) + (s_w[6][lane] + s_w[7][lane]));
+}
+inline int launch_sum_partials(const float* part, int S, int64_t L, float* out, cudaStream_t st) {
+  k_sum_partials<<<static_cast<unsigned>(ceil_div(L, 32)), 256, 0, st>>>(part, S, L, out);
+  DSMIL_LAUNCH_OK("k_sum_partials");
+  return 0;
 }
 
+inline bool tn_use_gemv(int M1, int M2) { return M1 <= kGemvMaxM1 && (M2 & 3) == 0 && (M2 >> 2) <= 256; }
 inline int tn_splits(int M1, int M2, int64_t N) {
-  const int tiles = ceil_div(M1, TBM) * ceil_div(M2, TBM);
-  int s = 296 / (tiles > 0 ? tiles : 1);
-  const int maxs = ceil_div(N, 128);
+  int s, maxs;
+  if (tn_use_gemv(M1, M2)) {
+    s = 296;
+    maxs = ceil_div(N, 64);
+  } else {
+    const int tiles = ceil_div(M1, TBM) * ceil_div(M2, TBM);
+    s = 296 / (tiles > 0 ? tiles : 1);
+    maxs = ceil_div(N, 128);
+  }
   if (s > maxs) s = maxs;
   if (s < 1) s = 1;
   return s;
@@ -208,15 +317,29 @@ inline int launch_gemm_tn(const float* P, int M1, const float* R, int M2, int64_
     return 0;
   }
   const int S = tn_splits(M1, M2, N);
-  int64_t rps = (N + S - 1) / S;
+  const int64_t L = static_cast<int64_t>(M1) * M2;
+  if (tn_use_gemv(M1, M2) && (reinterpret_cast<uintptr_t>(R) & 15) == 0 && (reinterpret_cast<uintptr_t>(part) & 15) == 0) {
+    const int64_t rps = (N + S - 1) / S;
+    switch (M1) {
+      case 1: k_gemv_tn<1><<<S, 256, 0, st>>>(P, R, M2, N, rps, part); break;
+      case 2: k_gemv_tn<2><<<S, 256, 0, st>>>(P, R, M2, N, rps, part); break;
+      case 3: k_gemv_tn<3><<<S, 256, 0, st>>>(P, R, M2, N, rps, part); break;
+      default: k_gemv_tn<4><<<S, 256, 0, st>>>(P, R, M2, N, rps, part); break;
+    }
+    DSMIL_LAUNCH_OK("k_gemv_tn");
+    return launch_sum_partials(part, S, L, out, st);
+  }
+  int Sg = S;
+  if (tn_use_gemv(M1, M2)) {                                 // unaligned operand: the tile kernel, within the same budget
+    const int tiles = ceil_div(M1, TBM) * ceil_div(M2, TBM);
+    Sg = std::max(1, std::min(S, 296 / tiles));
+  }
+  int64_t rps = (N + Sg - 1) / Sg;
   rps = (rps + TBK - 1) / TBK * TBK;
-  dim3 grid(ceil_div(M2, TBM), ceil_div(M1, TBM), S);
+  dim3 grid(ceil_div(M2, TBM), ceil_div(M1, TBM), Sg);
   k_gemm_tn<<<grid, 256, 0, st>>>(P, M1, R, M2, N, rps, part);
   DSMIL_LAUNCH_OK("k_gemm_tn");
-  const int64_t L = static_cast<int64_t>(M1) * M2;
-  k_sum_partials<<<ceil_div(L, 256), 256, 0, st>>>(part, S, L, out);
-  DSMIL_LAUNCH_OK("k_sum_partials");
-  return 0;
+  return launch_sum_partials(part, Sg, L, out, st);
 }
 inline int colsum_splits(int64_t N) {
   int s = ceil_div(N, 64);
@@ -231,9 +354,7 @@ inline int launch_colsum(const float* P, int M, int64_t N, float* part, float* o
   const int64_t rps = (N + S - 1) / S;
   k_colsum<<<S, 256, 0, st>>>(P, M, N, rps, part);
   DSMIL_LAUNCH_OK("k_colsum");
-  k_sum_partials<<<ceil_div(M, 256), 256, 0, st>>>(part, S, M, out);
-  DSMIL_LAUNCH_OK("k_sum_partials");
-  return 0;
+  return launch_sum_partials(part, S, M, out, st);
 }
 
 }  // namespace dsmil
