@@ -173,6 +173,20 @@ class _Staging:
             raise RuntimeError(f"JPEG decode of {names[i]} failed on the device: {jpeg.STATUS.get(int(st[i]), int(st[i]))}")
 
 
+_STAGING = {}       # (device, batch, H, W, layout) -> _Staging: pinned + device buffers are reused from bag to bag
+
+
+def _staging(batch, H, W, dev, fmt) -> "_Staging":
+    key = (str(dev), batch, H, W, str(fmt))
+    st = _STAGING.get(key)
+    if st is None:
+        if len(_STAGING) >= 2:                               # e.g. the two magnifications of tree mode; no unbounded growth
+            _STAGING.pop(next(iter(_STAGING)))
+        st = _STAGING[key] = _Staging(batch, H, W, dev, fmt)
+    st.status_names = [None, None]
+    return st
+
+
 def jpeg_route() -> str:
     r = os.environ.get("DSMIL_B200_JPEG", "auto")
     if r not in ("auto", "gpu", "host"):
@@ -261,8 +275,11 @@ def embed_bag(paths: Sequence[str], i_classifier, batch_size: int = 128, num_wor
             fe.to(memory_format=torch.channels_last)
             fe._dsmil_channels_last = True
     route = jpeg_route()
-    first = _decode_u8(paths[0])
-    H, W = first.shape[:2]
+    head = jpeg.parse_paths(paths[:1])                       # geometry of the bag from the first file's header
+    if head.statuses[0] == 0:
+        H, W = head.H, head.W
+    else:                                                    # not a file the parser reads: let PIL say what it is
+        H, W = _decode_u8(paths[0]).shape[:2]
     batches = [paths[i:i + batch_size] for i in range(0, len(paths), batch_size)]
     full_batches = sum(1 for b in batches if len(b) == batch_size)
     feats_out, cls_out = [], []
@@ -271,7 +288,7 @@ def embed_bag(paths: Sequence[str], i_classifier, batch_size: int = 128, num_wor
         if os.environ.get("DSMIL_B200_EMBED_GRAPH", "1") != "0" and full_batches >= 4:
             graphed = _graphed(i_classifier, batch_size, H, W, dev, fmt)     # before any other thread touches CUDA
         with ThreadPoolExecutor(max_workers=max(1, num_workers)) as pool, ThreadPoolExecutor(max_workers=1) as stager:
-            st = _Staging(batch_size, H, W, dev, fmt)
+            st = _staging(batch_size, H, W, dev, fmt)
             compute = torch.cuda.current_stream()
             for s in range(2):
                 st.consumed[s].record(compute)
