@@ -1,19 +1,20 @@
 #!/bin/bash
 mkdir -p gpurun_out
 cd /root/repo
-timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -12 > gpurun_out/r2_pytest_gpu_final2.txt
-cat gpurun_out/r2_pytest_gpu_final2.txt
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-( time timeout 900 python bench.py ) > gpurun_out/r2_bench_1gpu_final2.json 2> gpurun_out/r2_bench_1gpu_final2.err
-tail -4 gpurun_out/r2_bench_1gpu_final2.err
+timeout 900 python -m pytest tests/test_zz_jpeg_gpu.py tests/test_zz_tree_gpu.py -x -q -k "embed_bag or tree" 2>&1 | tail -4 > gpurun_out/r2_jpeg_embed_pytest.txt
+cat gpurun_out/r2_jpeg_embed_pytest.txt
+timeout 600 python - > gpurun_out/r2_files_leg.json 2> gpurun_out/r2_files_leg.err <<'PY'
+import json, sys, torch
+sys.path.insert(0, '/root/repo')
+import bench
+dev = torch.device('cuda', 0)
+torch.cuda.set_device(0)
+refmod = bench.load_reference_module()
+print(json.dumps({"embed_from_files": bench.files_leg(dev, refmod)}, indent=1))
+PY
+grep -v "Computed" gpurun_out/r2_files_leg.err | tail -5 | cut -c1-300
 python - <<'PY'
 import json
-d=json.loads([l for l in open('gpurun_out/r2_bench_1gpu_final2.json') if l.startswith('{')][-1])
-ex=d.get('extras',{})
-print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['roofline']['frac'], d['e2e']['value'])
-print('train', ex.get('train_n15000_c1'))
-print('embed', {k:v for k,v in ex.get('embed_resnet18_in',{}).items() if k in ('value','ms_per_batch','ms_per_batch_nchw','speedup','unavailable')})
-ef=ex.get('embed_from_files',{})
-print('files', ef.get('compute_feats', ef))
-print('agg', d.get('embed_aggregate_resnet18'))
+d=json.load(open('gpurun_out/r2_files_leg.json'))
+print(json.dumps(d["embed_from_files"]["compute_feats"], indent=1))
 PY
